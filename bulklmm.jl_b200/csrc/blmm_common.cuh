@@ -1,0 +1,92 @@
+// Shared device helpers for libblmm_b200 (sm_100a only): mbarrier / bulk-async-copy (TMA engine)
+// PTX wrappers, the FP64 tensor-core atom, warp reductions, and the operand layout constants.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace blmm {
+
+// ---------------------------------------------------------------------------------------------
+// Operand layout ("K-chunked panels").
+// Both GEMM operands are K-contiguous vectors of length n (a trait or a marker).  They are stored
+// as [q][col][KC] with KC = 20 doubles per K-chunk: a tile of consecutive columns of one chunk is
+// ONE contiguous block (a single bulk async copy), and a row stride of 20 doubles makes the DMMA
+// fragment loads (8 rows x 4 consecutive doubles per warp) shared-memory bank-conflict free
+// (20*2 mod 32 = 8: the four rows of a half-warp land on four disjoint 8-bank groups).
+// ---------------------------------------------------------------------------------------------
+constexpr int KC = 20;
+constexpr int MAXC = 8;      // covariate columns incl. intercept handled by the register paths
+
+__host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline int num_kchunks(int64_t n) { return (int)((n + KC - 1) / KC); }
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// 1-D bulk asynchronous copy global -> shared through the TMA engine (SASS: UBLKCP), completion
+// counted in bytes on an mbarrier.  dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// FP64 tensor-core atom: D(8x8) += A(8x4, row) * B(4x8, col).  Lane l = 4*g + t holds
+// a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1].  SASS: DMMA.8x8x4.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void st_global_v2(double* p, double a, double b) {
+  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+
+// max over non-negative doubles (bit pattern order == numeric order); NaN propagates as "large".
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+}  // namespace blmm
