@@ -1,0 +1,393 @@
+"""Host-side mirror of BulkLMM.jl's public API for the multi-trait genome-scan path, on top of the
+C-ABI of libblmm_b200.so.
+
+Julia is not installed in the build image, so this Python layer stands where the Julia shim
+(bulklmm.jl_b200/julia/BulkLMMB200.jl) stands in production: same function names, keyword
+arguments, defaults, result fields and error strings as the reference
+
+    bulkscan / bulkscan_null_grid / bulkscan_alt_grid / bulkscan_null   src/bulkscan.jl:81-526
+    scan(...; permutation_test=true, nperms, rndseed)                   src/scan.jl:94-271, 485-557
+    calcKinship                                                         src/kinship.jl:4-14
+    transform_rotation                                                  src/transform_helpers.jl:1-54
+    get_thresholds                               src/analysis_helpers/single_trait_analysis.jl:13-23
+
+All compute happens in the CUDA library; what is done here is argument plumbing (intercept column,
+observation-weight pre-scaling, column-major staging).  Matrices are n x m (traits), n x p
+(markers), results p x m, exactly as in Julia.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+class BlmmError(Exception):
+    """Mirrors Julia `error(msg)`: `.msg` is the reference's string, `.code` the BLMM_E_* status."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+        self.msg = msg
+
+
+def _f(a) -> np.ndarray:
+    """float64, column-major (Julia layout)."""
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One context = one GPU (blmm_create).  Not thread-safe: one call in flight per engine."""
+
+    def __init__(self, device: int = 0):
+        self.lib = L.load()
+        h = C.c_void_p()
+        st = self.lib.blmm_create(C.byref(h), int(device))
+        if st != L.OK:
+            raise BlmmError(st, "blmm_create failed: no usable sm_100 (B200) device" if st == L.E_NO_DEVICE
+                            else f"blmm_create failed with status {st}")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.blmm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def _check(self, st: int):
+        if st != L.OK:
+            raise BlmmError(st, self.lib.blmm_last_error(self.h).decode())
+
+    def sync(self):
+        self._check(self.lib.blmm_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.blmm_stream(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.blmm_launch_count(self.h))
+
+    def set_profiling(self, on: bool):
+        self.lib.blmm_set_profiling(self.h, int(on))
+
+    def last_scan_ms(self) -> float:
+        return float(self.lib.blmm_last_scan_ms(self.h))
+
+    @staticmethod
+    def make_opts(method=L.METHOD_NULL_GRID, reml=False, prior_variance=1.0, prior_sample_size=0.0,
+                  h2_grid=None, optim_interval=1, h2_panel_mode=L.H2PANEL_REFERENCE, mem_space=L.MEM_HOST,
+                  ld_out=0):
+        o = L.Opts()
+        o.method = method
+        o.reml = int(bool(reml))
+        o.prior_variance = float(prior_variance)
+        o.prior_sample_size = float(prior_sample_size)
+        keep = None
+        if h2_grid is not None:
+            keep = np.ascontiguousarray(np.asarray(h2_grid, dtype=np.float64))
+            o.h2_grid = keep.ctypes.data_as(L.c_double_p)
+            o.ngrid = keep.shape[0]
+        o.optim_interval = int(optim_interval)
+        o.h2_panel_mode = h2_panel_mode
+        o.mem_space = mem_space
+        o.ld_out = ld_out
+        return o, keep
+
+    @staticmethod
+    def make_problem(n, p, m, c, Y, G, Covar, U, lam):
+        """Raw-pointer problem (ints are addresses: host numpy `.ctypes.data` or device `data_ptr()`)."""
+        pr = L.Problem()
+        pr.n, pr.p, pr.m, pr.c = n, p, m, c
+        pr.Y, pr.G, pr.Covar, pr.U, pr.lam = Y, G, Covar, U, lam
+        return pr
+
+    def _host_problem(self, Y, G, Covar, U, lam):
+        n = Covar.shape[0]
+        m = 0 if Y is None else Y.shape[1]
+        p = 0 if G is None else G.shape[1]
+        pr = self.make_problem(n, p, m, Covar.shape[1],
+                               None if Y is None else Y.ctypes.data, None if G is None else G.ctypes.data,
+                               Covar.ctypes.data, U.ctypes.data, lam.ctypes.data)
+        return pr
+
+    # -- setup ---------------------------------------------------------------------------------
+    def calc_kinship(self, G) -> np.ndarray:
+        G = _f(G)
+        n, p = G.shape
+        K = np.empty((n, n), order="F")
+        self._check(self.lib.blmm_kinship(self.h, n, p, _ptr(G), _ptr(K), L.MEM_HOST))
+        return K
+
+    def decompose(self, K, decomp_scheme: str = "eigen"):
+        """(U, lambda): columns of U are eigenvectors (Ut = U.T).  Returns also #eigenvalues < -1e-7."""
+        if decomp_scheme not in ("eigen", "svd"):
+            raise BlmmError(L.E_INVALID, "Please choose either `eigen` or `svd` for decomposition of the kinship matrix.")
+        K = _f(K)
+        n = K.shape[0]
+        if K.shape[1] != n:
+            raise BlmmError(L.E_DIM, "Dimension mismatch.")
+        U = np.empty((n, n), order="F")
+        lam = np.empty(n)
+        nneg = C.c_int(0)
+        self._check(self.lib.blmm_decompose(self.h, n, _ptr(K), L.DECOMP_EIGEN if decomp_scheme == "eigen" else L.DECOMP_SVD,
+                                            _ptr(U), _ptr(lam), C.byref(nneg), L.MEM_HOST))
+        return U, lam, int(nneg.value)
+
+    def rotate(self, Y, X, U, lam):
+        """(Ut*Y, Ut*X) for a given decomposition."""
+        Y, X, U = _f(Y), _f(X), _f(U)
+        n = Y.shape[0]
+        pr = self.make_problem(n, 0, Y.shape[1], X.shape[1], Y.ctypes.data, None, X.ctypes.data, U.ctypes.data,
+                               np.ascontiguousarray(lam).ctypes.data)
+        Y0 = np.empty_like(Y, order="F")
+        X0 = np.empty_like(X, order="F")
+        self._check(self.lib.blmm_rotate(self.h, C.byref(pr), _ptr(Y0), _ptr(X0), L.MEM_HOST))
+        return Y0, X0
+
+    # -- the hot path (raw pointers: device-resident buffers, asynchronous until sync()) --------
+    def bulkscan_raw(self, pr, opts, L_ptr: int, h2_ptr: Optional[int]):
+        self._check(self.lib.blmm_bulkscan(self.h, C.byref(pr), C.byref(opts), C.c_void_p(L_ptr),
+                                           C.c_void_p(h2_ptr) if h2_ptr else None))
+
+    def scan_perms_raw(self, pr, opts, perm_ptr: int, nperms: int, lod_ptr: int, Lperms_ptr: Optional[int],
+                       max_ptr: Optional[int], s2_ptr: Optional[int], h2_ptr: Optional[int]):
+        vp = lambda a: C.c_void_p(a) if a else None
+        self._check(self.lib.blmm_scan_perms(self.h, C.byref(pr), C.byref(opts), vp(perm_ptr), nperms, vp(lod_ptr),
+                                             vp(Lperms_ptr), vp(max_ptr), vp(s2_ptr), vp(h2_ptr)))
+
+    # -- the hot path (host buffers) -----------------------------------------------------------
+    def bulkscan_host(self, Y, G, Covar, U, lam, method, h2_grid, reml, prior_variance, prior_sample_size,
+                      optim_interval=1, h2_panel_mode=L.H2PANEL_REFERENCE, want_h2=True):
+        Y, G, Covar, U = _f(Y), _f(G), _f(Covar), _f(U)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        p, m = G.shape[1], Y.shape[1]
+        pr = self._host_problem(Y, G, Covar, U, lam)
+        o, keep = self.make_opts(method=method, reml=reml, prior_variance=prior_variance,
+                                 prior_sample_size=prior_sample_size, h2_grid=h2_grid,
+                                 optim_interval=optim_interval, h2_panel_mode=h2_panel_mode)
+        Lout = np.empty((p, m), order="F")
+        if method == L.METHOD_ALT_GRID:
+            H = np.empty((p, m), order="F") if want_h2 else None
+        else:
+            H = np.empty(m) if want_h2 else None
+        self._check(self.lib.blmm_bulkscan(self.h, C.byref(pr), C.byref(o), _ptr(Lout), _ptr(H)))
+        return Lout, H
+
+    def grid_loglik(self, Y, Covar, U, lam, h2_grid, reml=False, prior_variance=1.0, prior_sample_size=0.0):
+        Y, Covar, U = _f(Y), _f(Covar), _f(U)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        pr = self._host_problem(Y, None, Covar, U, lam)
+        o, keep = self.make_opts(reml=reml, prior_variance=prior_variance, prior_sample_size=prior_sample_size,
+                                 h2_grid=h2_grid)
+        ell = np.empty((len(keep), Y.shape[1]), order="F")
+        self._check(self.lib.blmm_grid_loglik(self.h, C.byref(pr), C.byref(o), _ptr(ell)))
+        return ell
+
+    def fit_h2(self, Y, Covar, U, lam, reml=False, prior_variance=0.0, prior_sample_size=0.0, optim_interval=1):
+        Y, Covar, U = _f(Y), _f(Covar), _f(U)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        m = Y.shape[1]
+        pr = self._host_problem(Y, None, Covar, U, lam)
+        o, _ = self.make_opts(reml=reml, prior_variance=prior_variance, prior_sample_size=prior_sample_size,
+                              optim_interval=optim_interval)
+        h2, s2, ell = np.empty(m), np.empty(m), np.empty(m)
+        self._check(self.lib.blmm_fit_h2(self.h, C.byref(pr), C.byref(o), _ptr(h2), _ptr(s2), _ptr(ell)))
+        return h2, s2, ell
+
+    def scan_perms_host(self, y, G, Covar, U, lam, perm_idx, reml=False, prior_variance=0.0,
+                        prior_sample_size=0.0, optim_interval=1, want_L=True, want_max=True):
+        y, G, Covar, U = _f(y), _f(G), _f(Covar), _f(U)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        perm_idx = np.asfortranarray(np.asarray(perm_idx, dtype=np.int32))
+        n, p = G.shape
+        if perm_idx.ndim != 2 or (perm_idx.shape[1] > 0 and perm_idx.shape[0] != n):
+            raise BlmmError(L.E_DIM, "Dimension mismatch.")
+        nperms = perm_idx.shape[1]
+        pr = self._host_problem(y, G, Covar, U, lam)
+        o, _ = self.make_opts(reml=reml, prior_variance=prior_variance, prior_sample_size=prior_sample_size,
+                              optim_interval=optim_interval)
+        lod = np.empty(p)
+        Lp = np.empty((p, nperms), order="F") if want_L else None
+        mx = np.empty(nperms) if want_max else None
+        s2, h2 = np.empty(1), np.empty(1)
+        self._check(self.lib.blmm_scan_perms(self.h, C.byref(pr), C.byref(o), _ptr(perm_idx), nperms, _ptr(lod),
+                                             _ptr(Lp), _ptr(mx), _ptr(s2), _ptr(h2)))
+        return SimpleNamespace(sigma2_e=float(s2[0]), h2_null=float(h2[0]), lod=lod, L_perms=Lp, max_lod=mx)
+
+
+_default_engine: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine
+
+
+# ---------------------------------------------------------------------------------------------
+# Reference-shaped functions
+# ---------------------------------------------------------------------------------------------
+def calcKinship(geno, engine: Optional[Engine] = None) -> np.ndarray:
+    """src/kinship.jl:4-14."""
+    return (engine or default_engine()).calc_kinship(geno)
+
+
+def transform_rotation(y, g, K, addIntercept: bool = True, decomp_scheme: str = "eigen",
+                       engine: Optional[Engine] = None):
+    """src/transform_helpers.jl:1-54 -> (Ut*y, Ut*X, lambda)."""
+    eng = engine or default_engine()
+    y, g = _f(y), _f(g)
+    n = y.shape[0]
+    if g.shape[0] != n or np.asarray(K).shape[0] != n:
+        raise BlmmError(L.E_DIM, "Dimension mismatch.")
+    X = np.hstack([np.ones((n, 1)), g]) if addIntercept else g
+    U, lam, _ = eng.decompose(K, decomp_scheme)
+    Y0, X0 = eng.rotate(y, X, U, lam)
+    return Y0, X0, lam
+
+
+def _prep(Y, G, Covar, K, weights, addIntercept):
+    """The argument plumbing shared by the bulkscan methods: default intercept-only covariates
+    (3-argument forms, src/bulkscan.jl:94-109), intercept column, and the observation-weight
+    pre-scaling block (src/bulkscan.jl:231-250, 351-370, 457-476)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim == 1:
+        Y = Y.reshape(-1, 1)
+    G = np.asarray(G, dtype=np.float64)
+    K = np.asarray(K, dtype=np.float64)
+    n = Y.shape[0]
+    if G.shape[0] != n or K.shape[0] != n or K.shape[1] != n:
+        raise BlmmError(L.E_DIM, "Dimension mismatch.")
+    if Covar is None:
+        C0 = np.ones((n, 1))
+    else:
+        Covar = np.asarray(Covar, dtype=np.float64).reshape(n, -1)
+        C0 = np.hstack([np.ones((n, 1)), Covar]) if addIntercept else Covar
+    if weights is not None:
+        W = np.asarray(weights, dtype=np.float64)
+        Y = W[:, None] * Y
+        G = W[:, None] * G
+        C0 = W[:, None] * C0
+        K = W[:, None] * K * W[None, :]
+    return Y, G, C0, K
+
+
+_METHODS = {"null-grid": L.METHOD_NULL_GRID, "alt-grid": L.METHOD_ALT_GRID, "null-exact": L.METHOD_NULL_EXACT}
+
+
+def bulkscan(Y, G, K, Covar=None, method: str = "null-grid", h2_grid=None, nb: int = 1, nt_blas: int = 1,
+             addIntercept: bool = True, weights=None, prior_variance: float = 1.0,
+             prior_sample_size: float = 0.0, reml: bool = False, optim_interval: int = 1,
+             decomp_scheme: str = "eigen", output_pvals: bool = False, chisq_df: int = 1,
+             h2_panel_mode: str = "reference", decomposition=None, engine: Optional[Engine] = None):
+    """src/bulkscan.jl:81-162.  `nb` / `nt_blas` are accepted and ignored (CPU threading knobs).
+    `decomposition=(U, lambda)` skips the kinship eigendecomposition (blmm_decompose)."""
+    eng = engine or default_engine()
+    if method not in _METHODS:
+        raise BlmmError(L.E_INVALID, "unknown method: choose null-exact, null-grid or alt-grid")
+    if h2_grid is None:
+        h2_grid = np.arange(10) / 10.0  # collect(0.0:0.1:0.9), src/bulkscan.jl:82
+    Y, G, C0, K = _prep(Y, G, Covar, K, weights, addIntercept)
+    if decomposition is None:
+        U, lam, _ = eng.decompose(K, decomp_scheme)
+    else:
+        U, lam = decomposition
+    mode = L.H2PANEL_ARGMAX if h2_panel_mode == "argmax" else L.H2PANEL_REFERENCE
+    Lmat, H = eng.bulkscan_host(Y, G, C0, U, lam, _METHODS[method], h2_grid, reml, prior_variance,
+                                prior_sample_size, optim_interval=optim_interval, h2_panel_mode=mode)
+    out = SimpleNamespace(L=Lmat)
+    if method == "alt-grid":
+        out.h2_panel = H
+    else:
+        out.h2_null_list = H
+    if output_pvals:
+        out.log10Pvals_mat = lod2log10p(Lmat, chisq_df)
+        out.Chisq_df = chisq_df
+    return out
+
+
+def bulkscan_null_grid(Y, G, K, grid_list, Covar=None, **kw):
+    """src/bulkscan.jl:321-385 -> (L, h2_null_list)."""
+    return bulkscan(Y, G, K, Covar=Covar, method="null-grid", h2_grid=grid_list, **kw)
+
+
+def bulkscan_alt_grid(Y, G, K, hsq_list, Covar=None, **kw):
+    """src/bulkscan.jl:428-526 -> (L, h2_panel)."""
+    return bulkscan(Y, G, K, Covar=Covar, method="alt-grid", h2_grid=hsq_list, **kw)
+
+
+def bulkscan_null(Y, G, K, Covar=None, **kw):
+    """src/bulkscan.jl:188-314 -> (L, h2_null_list)."""
+    return bulkscan(Y, G, K, Covar=Covar, method="null-exact", **kw)
+
+
+def scan(y, g, K, covar=None, weights=None, prior_variance: float = 0.0, prior_sample_size: float = 0.0,
+         addIntercept: bool = True, reml: bool = False, assumption: str = "null", method: str = "qr",
+         optim_interval: int = 1, permutation_test: bool = False, nperms: int = 1024, rndseed: int = 0,
+         perm_idx=None, decomp_scheme: str = "eigen", decomposition=None, engine: Optional[Engine] = None):
+    """src/scan.jl:94-271 with permutation_test=true -> scan_perms_lite (src/scan.jl:485-557).
+
+    The shuffles are drawn on the host and cross the ABI as indices (`perm_idx`, n x nperms,
+    0-based).  In production the Julia shim draws them from MersenneTwister(rndseed) exactly as
+    the reference does; here numpy's generator seeded with `rndseed` stands in."""
+    eng = engine or default_engine()
+    y = np.asarray(y, dtype=np.float64)
+    if y.ndim == 1:
+        y = y.reshape(-1, 1)
+    if covar is None and not addIntercept:
+        raise BlmmError(L.E_INVALID, "Intercept has to be added when no other covariate is given.")
+    if assumption != "null":
+        raise BlmmError(L.E_INVALID, "Assumption keyword is not supported. Please enter null or alt.")
+    if not permutation_test:
+        raise BlmmError(L.E_INVALID, "scan without permutation_test is served by bulkscan(method=\"null-exact\")")
+    if y.shape[1] != 1:
+        raise BlmmError(L.E_ONE_TRAIT, "Can only handle one trait.")
+    y, g, C0, K = _prep(y, g, covar, K, weights, addIntercept)
+    n = y.shape[0]
+    if perm_idx is None:
+        from .synth import make_perm_indices
+        perm_idx = make_perm_indices(n, nperms, rndseed)
+    if decomposition is None:
+        U, lam, _ = eng.decompose(K, decomp_scheme)
+    else:
+        U, lam = decomposition
+    r = eng.scan_perms_host(y, g, C0, U, lam, perm_idx, reml=reml, prior_variance=prior_variance,
+                            prior_sample_size=prior_sample_size, optim_interval=optim_interval)
+    return r
+
+
+def get_thresholds(L_perms: np.ndarray, signif_level: Sequence[float]):
+    """src/analysis_helpers/single_trait_analysis.jl:13-23 (Julia `quantile` = type 7)."""
+    peaks = np.max(np.asarray(L_perms), axis=0)
+    probs = 1.0 - np.asarray(signif_level, dtype=np.float64)
+    return SimpleNamespace(probs=probs, thrs=np.quantile(peaks, probs))
+
+
+def thresholds_from_max(max_lod: np.ndarray, signif_level: Sequence[float]):
+    """get_thresholds from the per-permutation maxima the fused kernel returns (no L_perms needed)."""
+    probs = 1.0 - np.asarray(signif_level, dtype=np.float64)
+    return SimpleNamespace(probs=probs, thrs=np.quantile(np.asarray(max_lod), probs))
+
+
+def lod2log10p(lod, df: int = 1):
+    """src/util.jl:199-206 (host; the fused epilogue version is a later step)."""
+    from scipy.stats import chi2
+    return -chi2.logsf(np.asarray(lod) * 2.0 * np.log(10.0), df) / np.log(10.0)

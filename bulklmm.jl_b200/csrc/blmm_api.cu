@@ -1,0 +1,708 @@
+// C-ABI of libblmm_b200.so (include/blmm_b200.h): argument checking, workspace management, the
+// launch sequences of the scan methods, host<->device staging for BLMM_MEM_HOST calls.
+// No exception crosses the boundary; every entry point returns a BLMM_E_* status.
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/blmm_b200.h"
+#include "blmm_kernels.cuh"
+
+using namespace blmm;
+
+// workspace slots (grow-only device buffers owned by the context)
+enum Slot {
+  S_Y_IN, S_G_IN, S_C_IN, S_U_IN, S_LAM, S_GRID, S_Y0, S_C0, S_G0, S_YR, S_W, S_SW, S_Q, S_SLW, S_LDS,
+  S_ELL, S_RSS, S_BEST, S_ELLMAX, S_MOP, S_TOP, S_E, S_ET, S_BINS, S_TILEK0, S_COLMAP, S_L, S_H2P, S_H2V,
+  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_COUNT
+};
+
+struct blmm_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  void* buf[S_COUNT] = {};
+  size_t cap[S_COUNT] = {};
+  int* d_flags = nullptr;
+  int* h_flags = nullptr;  // pinned
+  std::string err;
+  int64_t launches = 0;
+  int profiling = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool scan_timed = false;
+};
+
+namespace {
+
+struct Fail {
+  int code;
+  std::string msg;
+};
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      throw Fail{BLMM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)};              \
+  } while (0)
+
+template <typename T>
+T* ws(blmm_ctx* ctx, Slot s, size_t count) {
+  const size_t bytes = std::max<size_t>(count * sizeof(T), 256);
+  if (ctx->cap[s] < bytes) {
+    if (ctx->buf[s]) CUDA_TRY(cudaFree(ctx->buf[s]));
+    ctx->buf[s] = nullptr;
+    ctx->cap[s] = 0;
+    CUDA_TRY(cudaMalloc(&ctx->buf[s], bytes));
+    ctx->cap[s] = bytes;
+  }
+  return reinterpret_cast<T*>(ctx->buf[s]);
+}
+
+// device view of an input matrix: the caller's pointer (device mode) or a staged copy (host mode)
+const double* stage_in(blmm_ctx* ctx, Slot s, const double* p, size_t count, int mem_space) {
+  if (mem_space == BLMM_MEM_DEVICE) return p;
+  double* d = ws<double>(ctx, s, count);
+  CUDA_TRY(cudaMemcpyAsync(d, p, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return d;
+}
+
+void reset_flags(blmm_ctx* ctx) { CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(int), ctx->stream)); }
+
+// Blocks until the queued work is done and turns raised device flags into the reference's errors.
+void finish_and_check(blmm_ctx* ctx) {
+  CUDA_TRY(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaGetLastError());
+  if (ctx->h_flags[FLAG_WEIGHTS]) throw Fail{BLMM_E_WEIGHTS, "Some weights are not positive."};
+  if (ctx->h_flags[FLAG_NOT_SPD])
+    throw Fail{BLMM_E_NOT_SPD, "Covariate matrix is rank deficient (weighted Gram matrix not positive definite)."};
+  if (ctx->h_flags[FLAG_ZERO_NORM])
+    throw Fail{BLMM_E_ZERO_NORM, "Dividing by zeros: the input vector can not contain any zeros!"};
+}
+
+void check_problem(const blmm_problem* pr, bool need_markers, bool need_decomp = true) {
+  if (!pr) throw Fail{BLMM_E_INVALID, "problem is NULL"};
+  if (pr->n <= 0 || pr->m < 0 || pr->p < 0) throw Fail{BLMM_E_DIM, "Dimension mismatch."};
+  if (pr->c < 1 || pr->c > MAXC)
+    throw Fail{BLMM_E_INVALID, "covariate count c (including the intercept) must be in 1.." + std::to_string(MAXC)};
+  if (pr->c >= pr->n) throw Fail{BLMM_E_INVALID, "more covariates than subjects"};
+  if (!pr->Y && pr->m > 0) throw Fail{BLMM_E_INVALID, "Y is NULL"};
+  if (!pr->Covar) throw Fail{BLMM_E_INVALID, "Covar is NULL"};
+  if (need_markers && (!pr->G || pr->p <= 0)) throw Fail{BLMM_E_INVALID, "G is NULL or p == 0"};
+  if (need_decomp && (!pr->U || !pr->lambda)) throw Fail{BLMM_E_INVALID, "U / lambda is NULL (call blmm_decompose)"};
+  if (pr->n > (int64_t)1 << 20 || pr->p > (int64_t)1 << 30 || pr->m > (int64_t)1 << 30)
+    throw Fail{BLMM_E_INVALID, "problem too large"};
+}
+
+LikParams lik_of(const blmm_opts* o) { return LikParams{o->prior_variance, o->prior_sample_size, o->reml ? 1 : 0}; }
+
+// Rotated inputs of one call (device, padded column-major).
+struct Rotated {
+  int n, n_pad, nq, c;
+  int64_t m, p;
+  const double* lambda;
+  double *Y0, *C0, *G0;
+};
+
+Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool with_markers) {
+  Rotated R;
+  R.n = (int)pr->n;
+  R.nq = num_kchunks(pr->n);
+  R.n_pad = R.nq * KC;
+  R.c = (int)pr->c;
+  R.m = pr->m;
+  R.p = with_markers ? pr->p : 0;
+  const size_t n = (size_t)pr->n;
+  const double* dU = stage_in(ctx, S_U_IN, pr->U, n * n, mem_space);
+  R.lambda = stage_in(ctx, S_LAM, pr->lambda, n, mem_space);
+  const double* dC = stage_in(ctx, S_C_IN, pr->Covar, n * R.c, mem_space);
+  R.C0 = ws<double>(ctx, S_C0, (size_t)R.n_pad * R.c);
+  ctx->launches += launch_rotate(dU, dC, pr->n, R.C0, R.n_pad, R.n_pad, R.n, R.c, ctx->stream);
+  R.Y0 = nullptr;
+  if (R.m > 0) {
+    const double* dY = stage_in(ctx, S_Y_IN, pr->Y, n * (size_t)R.m, mem_space);
+    R.Y0 = ws<double>(ctx, S_Y0, (size_t)R.n_pad * R.m);
+    ctx->launches += launch_rotate(dU, dY, pr->n, R.Y0, R.n_pad, R.n_pad, R.n, R.m, ctx->stream);
+  }
+  R.G0 = nullptr;
+  if (with_markers) {
+    const double* dG = stage_in(ctx, S_G_IN, pr->G, n * (size_t)R.p, mem_space);
+    R.G0 = ws<double>(ctx, S_G0, (size_t)R.n_pad * R.p);
+    ctx->launches += launch_rotate(dU, dG, pr->n, R.G0, R.n_pad, R.n_pad, R.n, R.p, ctx->stream);
+  }
+  return R;
+}
+
+WeightConsts weight_ws(blmm_ctx* ctx, int nk, int n_pad, int c) {
+  WeightConsts wc;
+  wc.w = ws<double>(ctx, S_W, (size_t)(nk + 1) * n_pad);
+  wc.sw = ws<double>(ctx, S_SW, (size_t)(nk + 1) * n_pad);
+  wc.Q = ws<double>(ctx, S_Q, (size_t)(nk + 1) * c * n_pad);
+  wc.slw = ws<double>(ctx, S_SLW, nk + 1);
+  wc.lds = ws<double>(ctx, S_LDS, nk + 1);
+  return wc;
+}
+
+const double* upload_grid(blmm_ctx* ctx, const blmm_opts* o) {
+  if (!o->h2_grid || o->ngrid < 1) throw Fail{BLMM_E_INVALID, "h2_grid is NULL or empty"};
+  if (o->ngrid > 255) throw Fail{BLMM_E_INVALID, "h2 grids longer than 255 points are not supported"};
+  for (int k = 0; k < o->ngrid; ++k) {
+    const double h = o->h2_grid[k];
+    if (isinf(h / (1.0 - h))) throw Fail{BLMM_E_H2_ONE, "Heritability of 1 is not allowed."};
+  }
+  double* d = ws<double>(ctx, S_GRID, o->ngrid);
+  CUDA_TRY(cudaMemcpyAsync(d, o->h2_grid, o->ngrid * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return d;
+}
+
+void copy_out(blmm_ctx* ctx, double* dst, const double* src_dev, size_t count, int mem_space) {
+  if (!dst || dst == src_dev) return;
+  CUDA_TRY(cudaMemcpyAsync(dst, src_dev, count * sizeof(double),
+                           mem_space == BLMM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                           ctx->stream));
+}
+
+void run_scan(blmm_ctx* ctx, const ScanParams& P) {
+  if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  ctx->launches += launch_scan(P, ctx->sm_count, ctx->stream);
+  if (ctx->profiling) {
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->scan_timed = true;
+  }
+  CUDA_TRY(cudaGetLastError());
+}
+
+void require_resident(int nq) {
+  if (nq > scan_max_nq(1))
+    throw Fail{BLMM_E_INVALID, "n = " + std::to_string(nq * KC) +
+                                   " (padded) exceeds the shared-memory-resident scan kernel (n <= " +
+                                   std::to_string(scan_max_nq(1) * KC) + ")"};
+}
+
+// ---------------------------------------------------------------------------------------------
+int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, double* L_out, double* h2_out) {
+  check_problem(pr, true);
+  if (!L_out) throw Fail{BLMM_E_INVALID, "L_out is NULL"};
+  const bool alt = o->method == BLMM_METHOD_ALT_GRID;
+  const int ms = o->mem_space;
+  const int nk = o->ngrid;
+  const int64_t p = pr->p, m = pr->m;
+  const int64_t ld = o->ld_out ? o->ld_out : p;
+  if (ld < p) throw Fail{BLMM_E_INVALID, "ld_out < p"};
+  if (m == 0) return BLMM_OK;
+  reset_flags(ctx);
+  const double* d_grid = upload_grid(ctx, o);
+  Rotated R = rotate_inputs(ctx, pr, ms, true);
+  require_resident(R.nq);
+  WeightConsts wc = weight_ws(ctx, nk, R.n_pad, R.c);
+  ctx->launches += launch_weight_consts(d_grid, nk, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags, ctx->stream);
+
+  double* Yr = ws<double>(ctx, S_YR, (size_t)R.n_pad * m);
+  double* ell = ws<double>(ctx, S_ELL, (size_t)nk * m);
+  double* rss = ws<double>(ctx, S_RSS, (size_t)nk * m);
+  int* best = ws<int>(ctx, S_BEST, m);
+  double* ellmax = ws<double>(ctx, S_ELLMAX, m);
+  int* bins = ws<int>(ctx, S_BINS, 3 * 256 + 8);  // count[256] start[256] cursor[256] n_tiles
+  int* bin_count = bins, *bin_start = bins + 256, *bin_cursor = bins + 512, *n_tiles = bins + 768;
+  CUDA_TRY(cudaMemsetAsync(bins, 0, (3 * 256 + 8) * sizeof(int), ctx->stream));
+
+  // null-grid: h2_null_list is written straight into the caller's array in device mode
+  double* h2v = nullptr;
+  if (!alt && h2_out) h2v = (ms == BLMM_MEM_DEVICE) ? h2_out : ws<double>(ctx, S_H2V, m);
+  ctx->launches += launch_trait_stats(R.Y0, m, R.n, R.n_pad, R.c, nk, wc, lik_of(o), d_grid, Yr, ell, rss, best,
+                                      ellmax, h2v, alt ? nullptr : bin_count, ctx->d_flags, ctx->stream);
+
+  const int64_t p_pad = round_up(p, SCAN_MT);
+  double* Mop = ws<double>(ctx, S_MOP, (size_t)nk * R.n_pad * p_pad);
+  ctx->launches += launch_marker_operand(R.G0, p, p_pad, R.n, R.n_pad, R.c, nk, wc, Mop, ctx->d_flags, ctx->stream);
+
+  ScanParams P{};
+  P.Mop = Mop;
+  P.grid = d_grid;
+  P.nq = R.nq;
+  P.p = (int)p;
+  P.p_pad = (int)p_pad;
+  P.m = m;
+  P.half_n = (double)R.n / 2.0;
+  P.argmax_mode = (o->h2_panel_mode == BLMM_H2PANEL_ARGMAX) ? 1 : 0;
+  double* dL = (ms == BLMM_MEM_DEVICE) ? L_out : ws<double>(ctx, S_L, (size_t)p * m);
+  P.L = dL;
+  P.ldL = (ms == BLMM_MEM_DEVICE) ? ld : p;
+  double* dH = nullptr;
+  if (alt) {
+    const int64_t tcol_pad = round_up(m, SCAN_TT);
+    double* e = ws<double>(ctx, S_E, (size_t)nk * tcol_pad);
+    double* et = ws<double>(ctx, S_ET, (size_t)nk * tcol_pad);
+    ctx->launches += launch_alt_scalars(ell, rss, ellmax, m, tcol_pad, nk, R.n, e, et, ctx->stream);
+    double* Top = ws<double>(ctx, S_TOP, (size_t)R.n_pad * tcol_pad);
+    ctx->launches += launch_pack_traits(Yr, nullptr, m, tcol_pad, R.n_pad, Top, ctx->stream);
+    P.Top = Top;
+    P.e = e;
+    P.et = et;
+    P.tcol_pad = tcol_pad;
+    P.n_tiles_t = (int)(tcol_pad / SCAN_TT);
+    P.nk = nk;
+    if (h2_out) {
+      dH = (ms == BLMM_MEM_DEVICE) ? h2_out : ws<double>(ctx, S_H2P, (size_t)p * m);
+      P.H2 = dH;
+    }
+  } else {
+    const int64_t tcol_pad = round_up(m, SCAN_TT) + (int64_t)nk * SCAN_TT;
+    int* tile_k0 = ws<int>(ctx, S_TILEK0, tcol_pad / SCAN_TT);
+    int* col_map = ws<int>(ctx, S_COLMAP, tcol_pad);
+    double* et = ws<double>(ctx, S_ET, tcol_pad);
+    ctx->launches += launch_null_bins(best, rss, m, nk, SCAN_TT, tcol_pad, bin_count, bin_start, bin_cursor,
+                                      tile_k0, n_tiles, col_map, et, ctx->stream);
+    double* Top = ws<double>(ctx, S_TOP, (size_t)R.n_pad * tcol_pad);
+    ctx->launches += launch_pack_traits(Yr, col_map, m, tcol_pad, R.n_pad, Top, ctx->stream);
+    P.Top = Top;
+    P.et = et;
+    P.tile_k0 = tile_k0;
+    P.n_tiles_dev = n_tiles;
+    P.col_map = col_map;
+    P.tcol_pad = tcol_pad;
+    P.n_tiles_t = (int)(tcol_pad / SCAN_TT);
+    P.nk = 1;
+  }
+  run_scan(ctx, P);
+
+  if (ms == BLMM_MEM_HOST) {
+    CUDA_TRY(cudaMemcpy2DAsync(L_out, ld * sizeof(double), dL, p * sizeof(double), p * sizeof(double), m,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    if (dH)
+      CUDA_TRY(cudaMemcpy2DAsync(h2_out, ld * sizeof(double), dH, p * sizeof(double), p * sizeof(double), m,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    if (h2v) copy_out(ctx, h2_out, h2v, m, ms);
+    finish_and_check(ctx);
+  }
+  return BLMM_OK;
+}
+
+int grid_loglik(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, double* ell_out) {
+  check_problem(pr, false);
+  if (!ell_out) throw Fail{BLMM_E_INVALID, "ell_out is NULL"};
+  const int ms = o->mem_space, nk = o->ngrid;
+  const int64_t m = pr->m;
+  if (m == 0) return BLMM_OK;
+  reset_flags(ctx);
+  const double* d_grid = upload_grid(ctx, o);
+  Rotated R = rotate_inputs(ctx, pr, ms, false);
+  WeightConsts wc = weight_ws(ctx, nk, R.n_pad, R.c);
+  ctx->launches += launch_weight_consts(d_grid, nk, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags, ctx->stream);
+  double* Yr = ws<double>(ctx, S_YR, (size_t)R.n_pad * m);
+  double* ell = (ms == BLMM_MEM_DEVICE) ? ell_out : ws<double>(ctx, S_ELL, (size_t)nk * m);
+  double* rss = ws<double>(ctx, S_RSS, (size_t)nk * m);
+  int* best = ws<int>(ctx, S_BEST, m);
+  double* ellmax = ws<double>(ctx, S_ELLMAX, m);
+  ctx->launches += launch_trait_stats(R.Y0, m, R.n, R.n_pad, R.c, nk, wc, lik_of(o), d_grid, Yr, ell, rss, best,
+                                      ellmax, nullptr, nullptr, ctx->d_flags, ctx->stream);
+  if (ms == BLMM_MEM_HOST) {
+    copy_out(ctx, ell_out, ell, (size_t)nk * m, ms);
+    // a zero-norm trait is only an error for the scans (colDivide!), not for wls_multivar
+    CUDA_TRY(cudaMemsetAsync(ctx->d_flags + FLAG_ZERO_NORM, 0, sizeof(int), ctx->stream));
+    finish_and_check(ctx);
+  }
+  return BLMM_OK;
+}
+
+// Yr for m traits: rotation + unweighted residual on the covariates (weight slot 0 = OLS)
+double* residualised_traits(blmm_ctx* ctx, const Rotated& R, const blmm_opts* o) {
+  WeightConsts wc0 = weight_ws(ctx, 0, R.n_pad, R.c);
+  ctx->launches += launch_weight_consts(nullptr, 0, R.lambda, R.C0, R.n, R.n_pad, R.c, wc0, ctx->d_flags, ctx->stream);
+  double* Yr = ws<double>(ctx, S_YR, (size_t)R.n_pad * R.m);
+  double* ell = ws<double>(ctx, S_ELL, 1);
+  double* rss = ws<double>(ctx, S_RSS, 1);
+  int* best = ws<int>(ctx, S_BEST, R.m);
+  double* ellmax = ws<double>(ctx, S_ELLMAX, R.m);
+  ctx->launches += launch_trait_stats(R.Y0, R.m, R.n, R.n_pad, R.c, 0, wc0, lik_of(o), nullptr, Yr, ell, rss, best,
+                                      ellmax, nullptr, nullptr, ctx->d_flags, ctx->stream);
+  return Yr;
+}
+
+int fit_h2(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, double* h2_out, double* sigma2_out,
+           double* ell_out) {
+  check_problem(pr, false);
+  const int ms = o->mem_space;
+  const int64_t m = pr->m;
+  if (m == 0) return BLMM_OK;
+  if (o->optim_interval < 1) throw Fail{BLMM_E_INVALID, "optim_interval must be >= 1"};
+  reset_flags(ctx);
+  Rotated R = rotate_inputs(ctx, pr, ms, false);
+  double* Yr = residualised_traits(ctx, R, o);
+  const bool dev = ms == BLMM_MEM_DEVICE;
+  double* h2 = (dev && h2_out) ? h2_out : ws<double>(ctx, S_H2V, m);
+  double* s2 = (dev && sigma2_out) ? sigma2_out : ws<double>(ctx, S_SIG2, m);
+  double* el = (dev && ell_out) ? ell_out : ws<double>(ctx, S_ELLV, m);
+  ctx->launches += launch_fit_h2(Yr, m, R.n, R.n_pad, R.c, R.C0, R.lambda, lik_of(o), o->optim_interval, h2, s2, el,
+                                 ctx->d_flags, ctx->stream);
+  if (!dev) {
+    copy_out(ctx, h2_out, h2, m, ms);
+    copy_out(ctx, sigma2_out, s2, m, ms);
+    copy_out(ctx, ell_out, el, m, ms);
+    finish_and_check(ctx);
+  }
+  return BLMM_OK;
+}
+
+int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const int32_t* perm_idx, int64_t nperms,
+               double* lod_out, double* Lperms_out, double* maxlod_out, double* sigma2_out, double* h2_out) {
+  if (pr && pr->m != 1) throw Fail{BLMM_E_ONE_TRAIT, "Can only handle one trait."};
+  check_problem(pr, true);
+  if (nperms < 0 || (nperms > 0 && !perm_idx)) throw Fail{BLMM_E_INVALID, "perm_idx is NULL"};
+  if (!lod_out) throw Fail{BLMM_E_INVALID, "lod_out is NULL"};
+  if (o->optim_interval < 1) throw Fail{BLMM_E_INVALID, "optim_interval must be >= 1"};
+  const int ms = o->mem_space;
+  const bool dev = ms == BLMM_MEM_DEVICE;
+  const int64_t p = pr->p;
+  const int64_t ld = o->ld_out ? o->ld_out : p;
+  if (ld < p) throw Fail{BLMM_E_INVALID, "ld_out < p"};
+  reset_flags(ctx);
+  Rotated R = rotate_inputs(ctx, pr, ms, true);
+  require_resident(R.nq);
+  double* Yr = residualised_traits(ctx, R, o);
+  double* h2 = (dev && h2_out) ? h2_out : ws<double>(ctx, S_H2V, 1);
+  double* s2 = (dev && sigma2_out) ? sigma2_out : ws<double>(ctx, S_SIG2, 1);
+  ctx->launches += launch_fit_h2(Yr, 1, R.n, R.n_pad, R.c, R.C0, R.lambda, lik_of(o), o->optim_interval, h2, s2,
+                                 nullptr, ctx->d_flags, ctx->stream);
+  // transform_reweight at the fitted h2 (weight slot 0)
+  WeightConsts wc = weight_ws(ctx, 1, R.n_pad, R.c);
+  ctx->launches += launch_weight_consts(h2, 1, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags, ctx->stream);
+  double* z = ws<double>(ctx, S_Z, R.n_pad + 8);
+  double* zrss = z + R.n_pad;
+  ctx->launches += launch_null_residual(Yr, R.n, R.n_pad, R.c, wc, z, zrss, ctx->stream);
+  const int64_t p_pad = round_up(p, SCAN_MT);
+  double* Mop = ws<double>(ctx, S_MOP, (size_t)R.n_pad * p_pad);
+  ctx->launches += launch_marker_operand(R.G0, p, p_pad, R.n, R.n_pad, R.c, 1, wc, Mop, ctx->d_flags, ctx->stream);
+
+  const int64_t ncol = nperms + 1;
+  const int64_t tcol_pad = round_up(ncol, SCAN_TT);
+  const int32_t* d_perm = nullptr;
+  if (nperms > 0) {
+    if (dev) {
+      d_perm = perm_idx;
+    } else {
+      int32_t* dp = ws<int32_t>(ctx, S_PERM, (size_t)R.n * nperms);
+      CUDA_TRY(cudaMemcpyAsync(dp, perm_idx, (size_t)R.n * nperms * sizeof(int32_t), cudaMemcpyHostToDevice,
+                               ctx->stream));
+      d_perm = dp;
+    }
+  }
+  double* Top = ws<double>(ctx, S_TOP, (size_t)R.n_pad * tcol_pad);
+  ctx->launches += launch_pack_perms(z, zrss, d_perm, nperms, R.n, R.n_pad, tcol_pad, Top, ctx->stream);
+
+  ScanParams P{};
+  P.Top = Top;
+  P.Mop = Mop;
+  P.nq = R.nq;
+  P.p = (int)p;
+  P.p_pad = (int)p_pad;
+  P.m = ncol;
+  P.tcol_pad = tcol_pad;
+  P.n_tiles_t = (int)(tcol_pad / SCAN_TT);
+  P.nk = 1;
+  P.half_n = (double)R.n / 2.0;
+  double* d_lod = dev ? lod_out : ws<double>(ctx, S_L, (size_t)p * (Lperms_out ? ncol : 1));
+  P.L0 = d_lod;
+  double* d_Lp = nullptr;
+  if (Lperms_out && nperms > 0) d_Lp = dev ? Lperms_out : d_lod + p;
+  P.L = d_Lp;
+  P.ldL = dev ? ld : p;
+  double* d_max = nullptr;
+  if (maxlod_out && nperms > 0) {
+    d_max = dev ? maxlod_out : ws<double>(ctx, S_COLMAX, nperms);
+    CUDA_TRY(cudaMemsetAsync(d_max, 0, nperms * sizeof(double), ctx->stream));
+    P.colmax = d_max;
+  }
+  run_scan(ctx, P);
+  if (!dev) {
+    copy_out(ctx, lod_out, d_lod, p, ms);
+    if (d_Lp)
+      CUDA_TRY(cudaMemcpy2DAsync(Lperms_out, ld * sizeof(double), d_Lp, p * sizeof(double), p * sizeof(double), nperms,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_max) copy_out(ctx, maxlod_out, d_max, nperms, ms);
+    copy_out(ctx, h2_out, h2, 1, ms);
+    copy_out(ctx, sigma2_out, s2, 1, ms);
+    finish_and_check(ctx);
+  }
+  return BLMM_OK;
+}
+
+int kinship(blmm_ctx* ctx, int64_t n, int64_t p, const double* G, double* K_out, int ms) {
+  if (n <= 0 || p <= 0 || !G || !K_out) throw Fail{BLMM_E_INVALID, "bad kinship arguments"};
+  const double* dG = stage_in(ctx, S_G_IN, G, (size_t)n * p, ms);
+  double* part = ws<double>(ctx, S_KPART, kinship_workspace_doubles((int)n, p));
+  double* dK = (ms == BLMM_MEM_DEVICE) ? K_out : ws<double>(ctx, S_KIN, (size_t)n * n);
+  ctx->launches += launch_kinship(dG, (int)n, p, dK, part, ctx->stream);
+  CUDA_TRY(cudaGetLastError());
+  if (ms == BLMM_MEM_HOST) {
+    copy_out(ctx, K_out, dK, (size_t)n * n, ms);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  return BLMM_OK;
+}
+
+__global__ void permute_eig_kernel(const double* __restrict__ V, const double* __restrict__ lam,
+                                   const int* __restrict__ order, int n, int take_abs, double* __restrict__ U,
+                                   double* __restrict__ lam_out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n * n) return;
+  const int a = (int)(idx / n), b = (int)(idx % n);
+  U[idx] = V[(int64_t)order[a] * n + b];
+  if (b == 0) lam_out[a] = take_abs ? fabs(lam[order[a]]) : lam[order[a]];
+}
+
+int decompose(blmm_ctx* ctx, int64_t n, const double* K, int scheme, double* U_out, double* lambda_out,
+              int* nneg_out, int ms) {
+  if (n <= 0 || !K || !U_out || !lambda_out) throw Fail{BLMM_E_INVALID, "bad decompose arguments"};
+  if (scheme != BLMM_DECOMP_EIGEN && scheme != BLMM_DECOMP_SVD)
+    throw Fail{BLMM_E_INVALID, "Please choose either `eigen` or `svd` for decomposition of the kinship matrix."};
+  if (!ctx->solver) {
+    if (cusolverDnCreate(&ctx->solver) != CUSOLVER_STATUS_SUCCESS) throw Fail{BLMM_E_CUDA, "cusolverDnCreate failed"};
+    cusolverDnSetStream(ctx->solver, ctx->stream);
+  }
+  const size_t nn = (size_t)n * n;
+  double* V = ws<double>(ctx, S_EIGV, nn + n + 8);
+  double* lam = V + nn;
+  int* info = reinterpret_cast<int*>(lam + n);
+  CUDA_TRY(cudaMemcpyAsync(V, K, nn * sizeof(double),
+                           ms == BLMM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  int lwork = 0;
+  if (cusolverDnDsyevd_bufferSize(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, V, (int)n,
+                                  lam, &lwork) != CUSOLVER_STATUS_SUCCESS)
+    throw Fail{BLMM_E_CUDA, "cusolverDnDsyevd_bufferSize failed"};
+  double* work = ws<double>(ctx, S_SOLVER, lwork);
+  if (cusolverDnDsyevd(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)n, V, (int)n, lam, work,
+                       lwork, info) != CUSOLVER_STATUS_SUCCESS)
+    throw Fail{BLMM_E_CUDA, "cusolverDnDsyevd failed"};
+  ctx->launches += 1;
+  std::vector<double> hl(n);
+  int hinfo = 0;
+  CUDA_TRY(cudaMemcpyAsync(hl.data(), lam, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (hinfo != 0) throw Fail{BLMM_E_CUDA, "syevd did not converge (info = " + std::to_string(hinfo) + ")"};
+  if (nneg_out) {
+    int c = 0;
+    for (int64_t i = 0; i < n; ++i) c += hl[i] < -1e-7;
+    *nneg_out = c;
+  }
+  // eigen: ascending eigenvalues (LAPACK order).  svd: singular values |lambda| descending.
+  std::vector<int> order(n);
+  for (int64_t i = 0; i < n; ++i) order[i] = (int)i;
+  if (scheme == BLMM_DECOMP_SVD)
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return fabs(hl[a]) > fabs(hl[b]); });
+  int* d_order = ws<int>(ctx, S_MISC, n);
+  CUDA_TRY(cudaMemcpyAsync(d_order, order.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  double* dU = (ms == BLMM_MEM_DEVICE) ? U_out : ws<double>(ctx, S_U_IN, nn);
+  double* dl = (ms == BLMM_MEM_DEVICE) ? lambda_out : ws<double>(ctx, S_LAM, n);
+  permute_eig_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, ctx->stream>>>(V, lam, d_order, (int)n,
+                                                                             scheme == BLMM_DECOMP_SVD, dU, dl);
+  ctx->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  if (ms == BLMM_MEM_HOST) {
+    copy_out(ctx, U_out, dU, nn, ms);
+    copy_out(ctx, lambda_out, dl, n, ms);
+  }
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `order` is a host temporary
+  return BLMM_OK;
+}
+
+int rotate(blmm_ctx* ctx, const blmm_problem* pr, double* Y0_out, double* X0_out, int ms) {
+  // transform_rotation accepts any number of columns in its second matrix (X = [1 g])
+  if (!pr || pr->n <= 0 || pr->m < 0 || pr->c < 0 || !pr->U) throw Fail{BLMM_E_DIM, "Dimension mismatch."};
+  if ((Y0_out && pr->m > 0 && !pr->Y) || (X0_out && pr->c > 0 && !pr->Covar))
+    throw Fail{BLMM_E_INVALID, "input matrix is NULL"};
+  const size_t n = (size_t)pr->n;
+  const double* dU = stage_in(ctx, S_U_IN, pr->U, n * n, ms);
+  if (Y0_out && pr->m > 0) {
+    const double* dY = stage_in(ctx, S_Y_IN, pr->Y, n * pr->m, ms);
+    double* out = (ms == BLMM_MEM_DEVICE) ? Y0_out : ws<double>(ctx, S_Y0, n * pr->m);
+    ctx->launches += launch_rotate(dU, dY, pr->n, out, pr->n, pr->n, (int)pr->n, pr->m, ctx->stream);
+    copy_out(ctx, Y0_out, out, n * pr->m, ms);
+  }
+  if (X0_out) {
+    const double* dC = stage_in(ctx, S_C_IN, pr->Covar, n * pr->c, ms);
+    const int64_t cols = pr->c + ((pr->G && pr->p > 0) ? pr->p : 0);
+    double* out = (ms == BLMM_MEM_DEVICE) ? X0_out : ws<double>(ctx, S_G0, n * cols);
+    ctx->launches += launch_rotate(dU, dC, pr->n, out, pr->n, pr->n, (int)pr->n, pr->c, ctx->stream);
+    if (cols > pr->c) {
+      const double* dG = stage_in(ctx, S_G_IN, pr->G, n * pr->p, ms);
+      ctx->launches += launch_rotate(dU, dG, pr->n, out + n * pr->c, pr->n, pr->n, (int)pr->n, pr->p, ctx->stream);
+    }
+    copy_out(ctx, X0_out, out, n * cols, ms);
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (ms == BLMM_MEM_HOST) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return BLMM_OK;
+}
+
+template <typename F>
+int guarded(blmm_ctx* ctx, F&& f) {
+  if (!ctx) return BLMM_E_INVALID;
+  try {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) throw Fail{BLMM_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
+    ctx->err.clear();
+    return f();
+  } catch (const Fail& fl) {
+    ctx->err = fl.msg;
+    cudaStreamSynchronize(ctx->stream);
+    cudaGetLastError();
+    return fl.code;
+  } catch (const std::exception& ex) {
+    ctx->err = ex.what();
+    return BLMM_E_INVALID;
+  } catch (...) {
+    ctx->err = "unknown failure";
+    return BLMM_E_INVALID;
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// extern "C" surface
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int blmm_abi_version(void) { return BLMM_ABI_VERSION; }
+
+int blmm_create(blmm_ctx** out, int device) {
+  if (!out) return BLMM_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return BLMM_E_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BLMM_E_NO_DEVICE;
+  if (prop.major != 10) return BLMM_E_NO_DEVICE;  // kernels are built for sm_100a only
+  blmm_ctx* ctx = new (std::nothrow) blmm_ctx();
+  if (!ctx) return BLMM_E_INVALID;
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  bool ok = cudaSetDevice(device) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMalloc(&ctx->d_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
+            cudaMallocHost(&ctx->h_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
+            cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
+  if (!ok) {
+    blmm_destroy(ctx);
+    return BLMM_E_CUDA;
+  }
+  *out = ctx;
+  return BLMM_OK;
+}
+
+void blmm_destroy(blmm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int s = 0; s < S_COUNT; ++s)
+    if (ctx->buf[s]) cudaFree(ctx->buf[s]);
+  if (ctx->d_flags) cudaFree(ctx->d_flags);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->solver) cusolverDnDestroy(ctx->solver);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* blmm_last_error(const blmm_ctx* ctx) { return ctx ? ctx->err.c_str() : "context is NULL"; }
+
+int blmm_sync(blmm_ctx* ctx) {
+  return guarded(ctx, [&] {
+    finish_and_check(ctx);
+    return BLMM_OK;
+  });
+}
+
+uint64_t blmm_stream(blmm_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+int64_t blmm_launch_count(const blmm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int blmm_set_profiling(blmm_ctx* ctx, int on) {
+  if (!ctx) return BLMM_E_INVALID;
+  ctx->profiling = on;
+  ctx->scan_timed = false;
+  return BLMM_OK;
+}
+
+double blmm_last_scan_ms(blmm_ctx* ctx) {
+  if (!ctx || !ctx->scan_timed) return -1.0;
+  float ms = -1.f;
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+int blmm_kinship(blmm_ctx* ctx, int64_t n, int64_t p, const double* G, double* K_out, int mem_space) {
+  return guarded(ctx, [&] { return kinship(ctx, n, p, G, K_out, mem_space); });
+}
+
+int blmm_decompose(blmm_ctx* ctx, int64_t n, const double* K, int scheme, double* U_out, double* lambda_out,
+                   int* nneg_out, int mem_space) {
+  return guarded(ctx, [&] { return decompose(ctx, n, K, scheme, U_out, lambda_out, nneg_out, mem_space); });
+}
+
+int blmm_rotate(blmm_ctx* ctx, const blmm_problem* prob, double* Y0_out, double* X0_out, int mem_space) {
+  return guarded(ctx, [&] { return rotate(ctx, prob, Y0_out, X0_out, mem_space); });
+}
+
+int blmm_bulkscan(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* L_out, double* h2_out) {
+  return guarded(ctx, [&] {
+    if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
+    switch (opts->method) {
+      case BLMM_METHOD_NULL_GRID:
+      case BLMM_METHOD_ALT_GRID:
+        return bulkscan_grid(ctx, prob, opts, L_out, h2_out);
+      case BLMM_METHOD_NULL_EXACT:
+        throw Fail{BLMM_E_INVALID, "method null-exact is not implemented yet"};
+      default:
+        throw Fail{BLMM_E_INVALID, "unknown method"};
+    }
+  });
+}
+
+int blmm_grid_loglik(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* ell_out) {
+  return guarded(ctx, [&] {
+    if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
+    return grid_loglik(ctx, prob, opts, ell_out);
+  });
+}
+
+int blmm_fit_h2(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* h2_out, double* sigma2_out,
+                double* ell_out) {
+  return guarded(ctx, [&] {
+    if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
+    return fit_h2(ctx, prob, opts, h2_out, sigma2_out, ell_out);
+  });
+}
+
+int blmm_scan_perms(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, const int32_t* perm_idx,
+                    int64_t nperms, double* lod_out, double* Lperms_out, double* maxlod_out, double* sigma2_out,
+                    double* h2_out) {
+  return guarded(ctx, [&] {
+    if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
+    return scan_perms(ctx, prob, opts, perm_idx, nperms, lod_out, Lperms_out, maxlod_out, sigma2_out, h2_out);
+  });
+}
+
+int blmm_scan_null(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* lod_out,
+                   double* sigma2_out, double* h2_out) {
+  (void)prob; (void)opts; (void)lod_out; (void)sigma2_out; (void)h2_out;
+  return guarded(ctx, [&]() -> int { throw Fail{BLMM_E_INVALID, "blmm_scan_null is not implemented yet"}; });
+}
+
+}  // extern "C"

@@ -16,6 +16,10 @@ namespace blmm {
 // ---------------------------------------------------------------------------------------------
 constexpr int KC = 20;
 constexpr int MAXC = 8;      // covariate columns incl. intercept handled by the register paths
+constexpr int NTRI = MAXC * (MAXC + 1) / 2;
+
+// device-side status flags (one int each), raised by kernels, read back by the host API
+enum Flag { FLAG_WEIGHTS = 0, FLAG_NOT_SPD = 1, FLAG_ZERO_NORM = 2, FLAG_COUNT = 8 };
 
 __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int num_kchunks(int64_t n) { return (int)((n + KC - 1) / KC); }
@@ -70,8 +74,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1].  SASS: DMMA.8x8x4.
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-      : "+d"(c0), "+d"(c1)
-      : "d"(a), "d"(b));
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -80,8 +84,10 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__device__ __forceinline__ void st_global_v2(double* p, double a, double b) {
-  asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+// streaming (evict-first) 8-byte store: the LOD / h2 panels are written once and never re-read
+// by the kernel, so they should not push the L2-resident marker operand out.
+__device__ __forceinline__ void st_stream(double* p, double v) {
+  asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
 // max over non-negative doubles (bit pattern order == numeric order); NaN propagates as "large".

@@ -1,0 +1,210 @@
+// Batched per-trait heritability fit: fitlmm (src/lmm.jl:56-86) = gridbrent (src/gridbrent.jl:9-24)
+// over Optim.jl's univariate Brent minimiser of -ell(h2), ell from wls (src/wls.jl:27-97).
+// One warp per trait; the n eigenvalue weights are spread over the lanes and every objective
+// evaluation is a handful of warp-shuffle reductions.  All lanes carry identical scalars (the
+// butterfly reduction is symmetric), so the Brent control flow is warp-uniform.
+#include <float.h>
+#include <math.h>
+
+#include "blmm_kernels.cuh"
+
+namespace blmm {
+
+namespace {
+
+constexpr int FIT_WARPS = 4;
+
+struct FitData {
+  const double* y;       // trait (residualised on C0, padded), length n_pad
+  const double* C0;      // [c][n_pad]
+  const double* lambda;  // [n]
+  int n, n_pad, c, lane;
+  LikParams lik;
+};
+
+// -ell(h2) and sigma2.  The covariate projection uses the Gram form S = C'WC, t = C'Wy,
+// rss = y'Wy - t'S^-1 t, log det S = 2 log|det R|, evaluated in one pass over the n weights.
+template <int C>
+__device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) {
+  constexpr int NT = C * (C + 1) / 2;
+  const double delta = h2 / (1.0 - h2);
+  double S[NT], t[C];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) S[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < C; ++i) t[i] = 0.0;
+  double yy = 0.0, slw = 0.0;
+  for (int l = d.lane; l < d.n; l += 32) {
+    const double w = 1.0 / (delta * d.lambda[l] + 1.0);
+    slw += log(w);
+    const double y = d.y[l];
+    const double wy = w * y;
+    yy = fma(wy, y, yy);
+    double cv[C];
+#pragma unroll
+    for (int a = 0; a < C; ++a) cv[a] = d.C0[(int64_t)a * d.n_pad + l];
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < C; ++a) {
+      t[a] = fma(cv[a], wy, t[a]);
+      const double wc = w * cv[a];
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        S[idx] = fma(wc, cv[b], S[idx]);
+        ++idx;
+      }
+    }
+  }
+  yy = warp_sum(yy);
+  slw = warp_sum(slw);
+#pragma unroll
+  for (int i = 0; i < NT; ++i) S[i] = warp_sum(S[i]);
+#pragma unroll
+  for (int i = 0; i < C; ++i) t[i] = warp_sum(t[i]);
+  // Cholesky S = L L' (packed lower, row-major), forward solve L u = t
+  double lds = 0.0, uu = 0.0;
+  double Lm[NT], u[C];
+#pragma unroll
+  for (int a = 0; a < C; ++a) {
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      double s = S[a * (a + 1) / 2 + b];
+#pragma unroll
+      for (int k = 0; k < b; ++k) s -= Lm[a * (a + 1) / 2 + k] * Lm[b * (b + 1) / 2 + k];
+      Lm[a * (a + 1) / 2 + b] = (a == b) ? sqrt(s) : s / Lm[b * (b + 1) / 2 + b];
+    }
+    double s = t[a];
+#pragma unroll
+    for (int k = 0; k < a; ++k) s -= Lm[a * (a + 1) / 2 + k] * u[k];
+    u[a] = s / Lm[a * (a + 1) / 2 + a];
+    uu = fma(u[a], u[a], uu);
+    lds += log(Lm[a * (a + 1) / 2 + a]);
+  }
+  lds *= 2.0;
+  const double rss = yy - uu;
+  const double a = d.lik.prior_a, b = d.lik.prior_b;
+  const double pdf = (b > 0.0) ? b + 2.0 : b;
+  const double ab = a * b;
+  const double denom = d.lik.reml ? ((double)(d.n - C) + pdf) : ((double)d.n + pdf);
+  const double sigma2 = (rss + ab) / denom;
+  double ll = -0.5 * (((double)d.n + b) * log(sigma2) - slw + (rss + ab) / sigma2);
+  if (d.lik.reml) ll += 0.5 * ((double)C * log(sigma2) - lds);
+  if (sigma2_out) *sigma2_out = sigma2;
+  return -ll;
+}
+
+__device__ double neg_loglik(const FitData& d, double h2, double* sigma2_out) {
+  switch (d.c) {
+    case 1: return neg_loglik_c<1>(d, h2, sigma2_out);
+    case 2: return neg_loglik_c<2>(d, h2, sigma2_out);
+    case 3: return neg_loglik_c<3>(d, h2, sigma2_out);
+    case 4: return neg_loglik_c<4>(d, h2, sigma2_out);
+    case 5: return neg_loglik_c<5>(d, h2, sigma2_out);
+    case 6: return neg_loglik_c<6>(d, h2, sigma2_out);
+    case 7: return neg_loglik_c<7>(d, h2, sigma2_out);
+    default: return neg_loglik_c<8>(d, h2, sigma2_out);
+  }
+}
+
+// Optim.jl `optimize(f, lo, hi, Brent())` with its defaults rel_tol = sqrt(eps), abs_tol = eps,
+// iterations = 1000 (call site src/gridbrent.jl:16).
+__device__ void brent(const FitData& d, double lo, double hi, double* xmin, double* fmin_out) {
+  const double golden = 0.5 * (3.0 - sqrt(5.0));
+  const double rel_tol = sqrt(DBL_EPSILON), abs_tol = DBL_EPSILON;
+  double x = lo + golden * (hi - lo);
+  double fx = neg_loglik(d, x, nullptr);
+  double step = 0.0, old_step = 0.0;
+  double xo = x, xoo = x, fo = fx, foo = fx;
+  for (int it = 0; it < 1000; ++it) {
+    double p = 0.0, q = 0.0;
+    const double tol = rel_tol * fabs(x) + abs_tol;
+    const double mid = (hi + lo) / 2.0;
+    if (fabs(x - mid) <= 2.0 * tol - (hi - lo) / 2.0) break;
+    if (fabs(old_step) > tol) {
+      const double r = (x - xo) * (fx - foo);
+      q = (x - xoo) * (fx - fo);
+      p = (x - xoo) * q - (x - xo) * r;
+      q = 2.0 * (q - r);
+      if (q > 0.0)
+        p = -p;
+      else
+        q = -q;
+    }
+    if (fabs(p) < fabs(q * old_step / 2.0) && p < q * (hi - x) && p < q * (x - lo)) {
+      old_step = step;
+      step = p / q;
+      const double xt = x + step;
+      if ((xt - lo) < 2.0 * tol || (hi - xt) < 2.0 * tol) step = (x < mid) ? tol : -tol;
+    } else {
+      old_step = (x < mid) ? (hi - x) : (lo - x);
+      step = golden * old_step;
+    }
+    const double xn = (fabs(step) >= tol) ? x + step : x + ((step > 0.0) ? tol : -tol);
+    const double fn = neg_loglik(d, xn, nullptr);
+    if (fn < fx) {
+      if (xn < x)
+        hi = x;
+      else
+        lo = x;
+      xoo = xo; foo = fo;
+      xo = x; fo = fx;
+      x = xn; fx = fn;
+    } else {
+      if (xn < x)
+        lo = xn;
+      else
+        hi = xn;
+      if (fn <= fo || xo == x) {
+        xoo = xo; foo = fo;
+        xo = xn; fo = fn;
+      } else if (fn <= foo || xoo == x || xoo == xo) {
+        xoo = xn; foo = fn;
+      }
+    }
+  }
+  *xmin = x;
+  *fmin_out = fx;
+}
+
+__global__ void __launch_bounds__(32 * FIT_WARPS)
+    fit_h2_kernel(const double* __restrict__ Yr, int64_t m, int n, int n_pad, int c, const double* __restrict__ C0,
+                  const double* __restrict__ lambda, LikParams lik, int optim_interval, double* __restrict__ h2_out,
+                  double* __restrict__ sigma2_out, double* __restrict__ ell_out) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * FIT_WARPS + wid;
+  if (j >= m) return;
+  FitData d{Yr + j * n_pad, C0, lambda, n, n_pad, c, lane, lik};
+  // gridbrent: points = range(0, 1, length = optim_interval + 1); keep the first of equal minima
+  double bx = 0.0, bf = INFINITY;
+  for (int i = 0; i < optim_interval; ++i) {
+    const double lo = (double)i / (double)optim_interval;
+    const double hi = (i + 1 == optim_interval) ? 1.0 : (double)(i + 1) / (double)optim_interval;
+    double x, f;
+    brent(d, lo, hi, &x, &f);
+    if (i == 0 || f < bf) {
+      bx = x;
+      bf = f;
+    }
+  }
+  double s2;
+  const double f = neg_loglik(d, bx, &s2);
+  if (lane == 0) {
+    if (h2_out) h2_out[j] = bx;
+    if (sigma2_out) sigma2_out[j] = s2;
+    if (ell_out) ell_out[j] = -f;
+  }
+}
+
+}  // namespace
+
+int launch_fit_h2(const double* Yr, int64_t m, int n, int n_pad, int c, const double* C0,
+                  const double* lambda, LikParams lik, int optim_interval, double* h2, double* sigma2,
+                  double* ell, int* flags, cudaStream_t stream) {
+  (void)flags;
+  const unsigned blocks = (unsigned)((m + FIT_WARPS - 1) / FIT_WARPS);
+  fit_h2_kernel<<<blocks, 32 * FIT_WARPS, 0, stream>>>(Yr, m, n, n_pad, c, C0, lambda, lik, optim_interval, h2,
+                                                       sigma2, ell);
+  return 1;
+}
+
+}  // namespace blmm

@@ -1,0 +1,567 @@
+// Preprocessing kernels of libblmm_b200: kinship, rotation by U', per-h2 weight constants, per-trait
+// null statistics, the weight-folded marker operand, null-grid binning and operand packing.
+// None of these is the roofline kernel (that is blmm_scan.cu); they touch each input O(1) times
+// and are written for coalesced access and no host round trips.
+#include <float.h>
+#include <math.h>
+
+#include "blmm_kernels.cuh"
+
+namespace blmm {
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 8;
+
+__device__ __forceinline__ double block_sum_128(double v, double* red) {
+  // blockDim.x == 128; returns the sum to every thread
+  v = warp_sum(v);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  return (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// -----------------------------------------------------------------------------------------------
+// FP64 SIMT GEMM tile (64 x 64 outputs, K step 16, 256 threads, 4 x 4 per thread) used by the two
+// setup products: rotation (A = U', B = X, both K-contiguous) and kinship ((G-1/2)(G-1/2)').
+// -----------------------------------------------------------------------------------------------
+constexpr int GT = 64, GK = 16;
+
+struct RotateOps {
+  const double* U;
+  const double* X;
+  int64_t ldx;
+  int n;
+  int64_t cols;
+  __device__ double a(int row, int k) const { return (row < n && k < n) ? U[(int64_t)k + (int64_t)row * n] : 0.0; }
+  __device__ double b(int k, int64_t col) const { return (col < cols && k < n) ? X[(int64_t)k + col * ldx] : 0.0; }
+};
+
+__global__ void __launch_bounds__(256) rotate_kernel(RotateOps op, double* __restrict__ out, int64_t ldo,
+                                                     int64_t ldo_zero) {
+  __shared__ double As[GK][GT + 1];
+  __shared__ double Bs[GK][GT + 1];
+  const int tid = threadIdx.x;
+  const int a0 = blockIdx.y * GT;
+  const int64_t c0 = (int64_t)blockIdx.x * GT;
+  const int tr = tid & 15, tc = tid >> 4;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < op.n; k0 += GK) {
+    {
+      const int kk = tid & 15, r = tid >> 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        As[kk][r + 16 * i] = op.a(a0 + r + 16 * i, k0 + kk);
+        Bs[kk][r + 16 * i] = op.b(k0 + kk, c0 + r + 16 * i);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][tr + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tc * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t col = c0 + tc * 4 + j;
+    if (col >= op.cols) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = a0 + tr + 16 * i;
+      if (row < ldo_zero) out[(int64_t)row + col * ldo] = (row < op.n) ? acc[i][j] : 0.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) kinship_partial_kernel(const double* __restrict__ G, int n, int64_t p,
+                                                              int64_t chunk, double* __restrict__ partial) {
+  __shared__ double As[GK][GT + 1];
+  __shared__ double Bs[GK][GT + 1];
+  const int tid = threadIdx.x;
+  const int a0 = blockIdx.y * GT, b0 = blockIdx.x * GT;
+  const int64_t i0 = (int64_t)blockIdx.z * chunk;
+  const int64_t i1 = (i0 + chunk < p) ? i0 + chunk : p;
+  const int tr = tid & 15, tc = tid >> 4;
+  double acc[4][4] = {};
+  for (int64_t k0 = i0; k0 < i1; k0 += GK) {
+    {
+      // the subject index is the contiguous one: let it be the fast thread index
+      const int r = tid & 63, kb = tid >> 6;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = kb + 4 * i;
+        const bool kin = (k0 + kk) < i1;
+        As[kk][r] = (kin && a0 + r < n) ? G[(int64_t)(a0 + r) + (k0 + kk) * n] - 0.5 : 0.0;
+        Bs[kk][r] = (kin && b0 + r < n) ? G[(int64_t)(b0 + r) + (k0 + kk) * n] - 0.5 : 0.0;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][tr + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tc * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  double* dst = partial + (int64_t)blockIdx.z * n * n;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int col = b0 + tc * 4 + j;
+    if (col >= n) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = a0 + tr + 16 * i;
+      if (row < n) dst[(int64_t)row + (int64_t)col * n] = acc[i][j];
+    }
+  }
+}
+
+__global__ void kinship_finish_kernel(const double* __restrict__ partial, int nsplit, int n, int64_t p,
+                                      double* __restrict__ K) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nn = (int64_t)n * n;
+  if (idx >= nn) return;
+  double s = 0.0;
+  for (int z = 0; z < nsplit; ++z) s += partial[(int64_t)z * nn + idx];  // fixed order: reproducible
+  const int a = (int)(idx % n), b = (int)(idx / n);
+  K[idx] = (a == b) ? 1.0 : 2.0 * s / (double)p + 0.5;
+}
+
+int kinship_nsplit(int n, int64_t p) {
+  const int64_t tiles = (int64_t)((n + GT - 1) / GT) * ((n + GT - 1) / GT);
+  int64_t ns = 592 / tiles;
+  const int64_t maxs = (p + 255) / 256;
+  if (ns > maxs) ns = maxs;
+  if (ns < 1) ns = 1;
+  return (int)ns;
+}
+
+// -----------------------------------------------------------------------------------------------
+// weight constants
+// -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) weight_consts_kernel(const double* __restrict__ h2_dev, int nk,
+                                                            const double* __restrict__ lambda,
+                                                            const double* __restrict__ C0, int n, int n_pad,
+                                                            int c, WeightConsts wc, int* flags) {
+  __shared__ double red[4];
+  __shared__ double Linv[MAXC][MAXC];
+  __shared__ double ldsum;
+  const int k = blockIdx.x;
+  const int tid = threadIdx.x;
+  const bool ols = (k == nk);
+  const double h2 = ols ? 0.0 : h2_dev[k];
+  const double delta = h2 / (1.0 - h2);
+  double* w = wc.w + (int64_t)k * n_pad;
+  double* sw = wc.sw + (int64_t)k * n_pad;
+  double* Q = wc.Q + (int64_t)k * c * n_pad;
+
+  double slw = 0.0;
+  for (int l = tid; l < n_pad; l += 128) {
+    double wv = 0.0;
+    if (l < n) {
+      wv = ols ? 1.0 : 1.0 / (delta * lambda[l] + 1.0);
+      if (!(wv > 0.0)) atomicExch(&flags[FLAG_WEIGHTS], 1);
+      slw += log(wv);
+    }
+    const double s = sqrt(wv);
+    w[l] = wv;
+    sw[l] = s;
+    for (int a = 0; a < c; ++a) Q[(int64_t)a * n_pad + l] = s * C0[(int64_t)a * n_pad + l];
+  }
+  slw = block_sum_128(slw, red);
+  if (tid == 0) {
+    wc.slw[k] = slw;
+    ldsum = 0.0;
+  }
+  // Cholesky-QR, applied twice: Q <- Q * inv(chol(Q'Q))'.  The second pass restores orthonormality
+  // to rounding level; log det(C0' W C0) accumulates over the passes.
+  for (int pass = 0; pass < 2; ++pass) {
+    double S[MAXC][MAXC];
+    for (int a = 0; a < c; ++a)
+      for (int b = 0; b <= a; ++b) {
+        double s = 0.0;
+        for (int l = tid; l < n_pad; l += 128) s = fma(Q[(int64_t)a * n_pad + l], Q[(int64_t)b * n_pad + l], s);
+        S[a][b] = block_sum_128(s, red);
+      }
+    if (tid == 0) {
+      // in-place lower Cholesky, then its inverse
+      bool ok = true;
+      double Lc[MAXC][MAXC];
+      for (int a = 0; a < c; ++a) {
+        for (int b = 0; b <= a; ++b) {
+          double s = S[a][b];
+          for (int t = 0; t < b; ++t) s -= Lc[a][t] * Lc[b][t];
+          if (a == b) {
+            if (!(s > 0.0)) ok = false;
+            Lc[a][a] = sqrt(s);
+          } else {
+            Lc[a][b] = s / Lc[b][b];
+          }
+        }
+      }
+      if (!ok) atomicExch(&flags[FLAG_NOT_SPD], 1);
+      double ld = 0.0;
+      for (int a = 0; a < c; ++a) ld += log(Lc[a][a]);
+      ldsum += 2.0 * ld;
+      for (int a = 0; a < c; ++a) {
+        for (int b = 0; b < c; ++b) Linv[a][b] = 0.0;
+        Linv[a][a] = 1.0 / Lc[a][a];
+        for (int b = 0; b < a; ++b) {
+          double s = 0.0;
+          for (int t = b; t < a; ++t) s -= Lc[a][t] * Linv[t][b];
+          Linv[a][b] = s / Lc[a][a];
+        }
+      }
+    }
+    __syncthreads();
+    for (int l = tid; l < n_pad; l += 128) {
+      for (int a = c - 1; a >= 0; --a) {
+        double s = 0.0;
+        for (int b = 0; b <= a; ++b) s = fma(Linv[a][b], Q[(int64_t)b * n_pad + l], s);
+        Q[(int64_t)a * n_pad + l] = s;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) wc.lds[k] = ldsum;
+}
+
+// ell of wls / wls_multivar (src/wls.jl:72-92) from the weighted rss
+__device__ __forceinline__ double null_loglik(double rss, double slw, double lds, int n, int c, LikParams lik,
+                                              double* sigma2_out) {
+  const double a = lik.prior_a, b = lik.prior_b;
+  const double pdf = (b > 0.0) ? b + 2.0 : b;
+  const double ab = a * b;
+  const double denom = lik.reml ? ((double)(n - c) + pdf) : ((double)n + pdf);
+  const double sigma2 = (rss + ab) / denom;
+  double ll = -0.5 * (((double)n + b) * log(sigma2) - slw + (rss + ab) / sigma2);
+  if (lik.reml) ll += 0.5 * ((double)c * log(sigma2) - lds);
+  if (sigma2_out) *sigma2_out = sigma2;
+  return ll;
+}
+
+// z = P_k (sw_k .* x): returns ||z||^2; the caller re-evaluates z_l through proj_elem.
+__device__ __forceinline__ void proj_coefs(const double* __restrict__ xb, const double* __restrict__ sw,
+                                           const double* __restrict__ Q, int n_pad, int c, int lane,
+                                           double coef[MAXC]) {
+#pragma unroll
+  for (int a = 0; a < MAXC; ++a) {
+    if (a < c) {
+      double s = 0.0;
+      for (int l = lane; l < n_pad; l += 32) s = fma(Q[(int64_t)a * n_pad + l], sw[l] * xb[l], s);
+      coef[a] = warp_sum(s);
+    }
+  }
+}
+__device__ __forceinline__ double proj_elem(const double* __restrict__ xb, const double* __restrict__ sw,
+                                            const double* __restrict__ Q, int n_pad, int c, int l,
+                                            const double coef[MAXC]) {
+  double z = sw[l] * xb[l];
+#pragma unroll
+  for (int a = 0; a < MAXC; ++a)
+    if (a < c) z = fma(-Q[(int64_t)a * n_pad + l], coef[a], z);
+  return z;
+}
+
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
+    trait_stats_kernel(const double* __restrict__ Y0, int64_t m, int n, int n_pad, int c, int nk, WeightConsts wc,
+                       LikParams lik, const double* __restrict__ grid_dev, double* __restrict__ Yr,
+                       double* __restrict__ ell, double* __restrict__ rss_out, int* __restrict__ best,
+                       double* __restrict__ ellmax, double* __restrict__ h2_out, int* bin_count, int* flags) {
+  extern __shared__ double smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wid;
+  if (j >= m) return;
+  double* yb = smem + (int64_t)wid * n_pad;
+  for (int l = lane; l < n_pad; l += 32) yb[l] = Y0[j * n_pad + l];
+  __syncwarp();
+  double coef[MAXC];
+  {
+    // unweighted residual on the covariates (slot nk: w = 1)
+    const double* sw1 = wc.sw + (int64_t)nk * n_pad;
+    const double* Qo = wc.Q + (int64_t)nk * c * n_pad;
+    proj_coefs(yb, sw1, Qo, n_pad, c, lane, coef);
+    for (int l = lane; l < n_pad; l += 32) {
+      const double y = proj_elem(yb, sw1, Qo, n_pad, c, l, coef);
+      yb[l] = y;
+      Yr[j * n_pad + l] = y;
+    }
+    __syncwarp();
+  }
+  double bestv = -INFINITY;
+  int bestk = 0;
+  for (int k = 0; k < nk; ++k) {
+    const double* sw = wc.sw + (int64_t)k * n_pad;
+    const double* Q = wc.Q + (int64_t)k * c * n_pad;
+    proj_coefs(yb, sw, Q, n_pad, c, lane, coef);
+    double s = 0.0;
+    for (int l = lane; l < n_pad; l += 32) {
+      const double z = proj_elem(yb, sw, Q, n_pad, c, l, coef);
+      s = fma(z, z, s);
+    }
+    const double rss = warp_sum(s);
+    const double ll = null_loglik(rss, wc.slw[k], wc.lds[k], n, c, lik, nullptr);
+    if (lane == 0) {
+      ell[(int64_t)k + j * nk] = ll;
+      rss_out[(int64_t)k * m + j] = rss;
+      if (!(sqrt(rss) > DBL_EPSILON)) atomicExch(&flags[FLAG_ZERO_NORM], 1);
+    }
+    if (k == 0 || ll > bestv) {  // strict: first maximum wins, as findmax
+      bestv = ll;
+      bestk = k;
+    }
+  }
+  if (lane == 0) {
+    best[j] = bestk;
+    ellmax[j] = bestv;
+    if (h2_out) h2_out[j] = grid_dev[bestk];
+    if (bin_count) atomicAdd(&bin_count[bestk], 1);
+  }
+}
+
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
+    marker_operand_kernel(const double* __restrict__ G0, int64_t p, int64_t p_pad, int n, int n_pad, int c, int nk,
+                          WeightConsts wc, double* __restrict__ Mop, int* flags) {
+  extern __shared__ double smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wid;
+  if (i >= p_pad) return;
+  const int nq = n_pad / KC;
+  if (i >= p) {
+    for (int k = 0; k < nk; ++k)
+      for (int l = lane; l < n_pad; l += 32)
+        Mop[(((int64_t)k * nq + l / KC) * p_pad + i) * KC + (l % KC)] = 0.0;
+    return;
+  }
+  double* gb = smem + (int64_t)wid * n_pad;
+  for (int l = lane; l < n_pad; l += 32) gb[l] = G0[i * n_pad + l];
+  __syncwarp();
+  double coef[MAXC];
+  for (int k = 0; k < nk; ++k) {
+    const double* sw = wc.sw + (int64_t)k * n_pad;
+    const double* Q = wc.Q + (int64_t)k * c * n_pad;
+    proj_coefs(gb, sw, Q, n_pad, c, lane, coef);
+    double s = 0.0;
+    for (int l = lane; l < n_pad; l += 32) {
+      const double z = proj_elem(gb, sw, Q, n_pad, c, l, coef);
+      s = fma(z, z, s);
+    }
+    const double nrm = sqrt(warp_sum(s));
+    if (lane == 0 && !(nrm > DBL_EPSILON)) atomicExch(&flags[FLAG_ZERO_NORM], 1);
+    const double inv = 1.0 / nrm;
+    for (int l = lane; l < n_pad; l += 32) {
+      const double z = proj_elem(gb, sw, Q, n_pad, c, l, coef);
+      Mop[(((int64_t)k * nq + l / KC) * p_pad + i) * KC + (l % KC)] = sw[l] * z * inv;
+    }
+  }
+}
+
+__global__ void alt_scalars_kernel(const double* __restrict__ ell, const double* __restrict__ rss,
+                                   const double* __restrict__ ellmax, int64_t m, int64_t tcol_pad, int nk,
+                                   double inv_half_n, double* __restrict__ e, double* __restrict__ et) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= tcol_pad) return;
+  if (j >= m) {
+    for (int k = 0; k < nk; ++k) {
+      e[(int64_t)k * tcol_pad + j] = 1.0;
+      et[(int64_t)k * tcol_pad + j] = 0.0;
+    }
+    return;
+  }
+  const double emax = ellmax[j];
+  for (int k = 0; k < nk; ++k) {
+    const double ev = exp(-(ell[(int64_t)k + j * nk] - emax) * inv_half_n);
+    e[(int64_t)k * tcol_pad + j] = ev;
+    et[(int64_t)k * tcol_pad + j] = ev / rss[(int64_t)k * m + j];
+  }
+}
+
+__global__ void bin_layout_kernel(const int* __restrict__ bin_count, int nk, int tile, int n_tiles_max,
+                                  int* bin_start, int* bin_cursor, int* tile_k0, int* n_tiles) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int pos = 0, t = 0;
+  for (int b = 0; b < nk; ++b) {
+    bin_start[b] = pos;
+    bin_cursor[b] = 0;
+    const int nt = (bin_count[b] + tile - 1) / tile;
+    for (int i = 0; i < nt; ++i) tile_k0[t++] = b;
+    pos += nt * tile;
+  }
+  *n_tiles = t;
+  for (; t < n_tiles_max; ++t) tile_k0[t] = 0;
+}
+
+__global__ void bin_scatter_kernel(const int* __restrict__ best, const double* __restrict__ rss, int64_t m,
+                                   const int* __restrict__ bin_start, int* bin_cursor, int* __restrict__ col_map,
+                                   double* __restrict__ et) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const int b = best[j];
+  const int pos = bin_start[b] + atomicAdd(&bin_cursor[b], 1);
+  col_map[pos] = (int)j;
+  et[pos] = 1.0 / rss[(int64_t)b * m + j];
+}
+
+__global__ void pack_traits_kernel(const double* __restrict__ Yr, const int* __restrict__ col_map, int64_t m,
+                                   int64_t tcol_pad, int n_pad, int64_t total, double* __restrict__ Top) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int kk = (int)(idx % KC);
+  const int64_t pos = (idx / KC) % tcol_pad;
+  const int q = (int)(idx / (KC * tcol_pad));
+  int64_t src = col_map ? (int64_t)col_map[pos] : (pos < m ? pos : -1);
+  Top[idx] = (src >= 0) ? Yr[src * n_pad + q * KC + kk] : 0.0;
+}
+
+__global__ void pack_perms_kernel(const double* __restrict__ z, const double* __restrict__ rss,
+                                  const int32_t* __restrict__ perm_idx, int64_t nperms, int n, int64_t tcol_pad,
+                                  int64_t total, double* __restrict__ Top) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int kk = (int)(idx % KC);
+  const int64_t s = (idx / KC) % tcol_pad;
+  const int q = (int)(idx / (KC * tcol_pad));
+  const int l = q * KC + kk;
+  double v = 0.0;
+  if (s <= nperms && l < n) {
+    const int src = (s == 0) ? l : perm_idx[(int64_t)l + (s - 1) * n];
+    v = z[src] / sqrt(*rss);
+  }
+  Top[idx] = v;
+}
+
+__global__ void __launch_bounds__(32) null_residual_kernel(const double* __restrict__ Yr, int n, int n_pad, int c,
+                                                           WeightConsts wc, double* __restrict__ z,
+                                                           double* __restrict__ rss) {
+  const int lane = threadIdx.x;
+  double coef[MAXC];
+  proj_coefs(Yr, wc.sw, wc.Q, n_pad, c, lane, coef);
+  double s = 0.0;
+  for (int l = lane; l < n_pad; l += 32) {
+    const double v = proj_elem(Yr, wc.sw, wc.Q, n_pad, c, l, coef);
+    z[l] = v;
+    s = fma(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) *rss = s;
+}
+
+}  // namespace
+
+// -----------------------------------------------------------------------------------------------
+// launchers
+// -----------------------------------------------------------------------------------------------
+int launch_rotate(const double* U, const double* X, int64_t ldx, double* out, int64_t ldo, int64_t ldo_zero,
+                  int n, int64_t cols, cudaStream_t stream) {
+  if (cols <= 0) return 0;
+  RotateOps op{U, X, ldx, n, cols};
+  dim3 grid((unsigned)((cols + GT - 1) / GT), (unsigned)((ldo_zero + GT - 1) / GT));
+  rotate_kernel<<<grid, 256, 0, stream>>>(op, out, ldo, ldo_zero);
+  return 1;
+}
+
+int64_t kinship_workspace_doubles(int n, int64_t p) { return (int64_t)kinship_nsplit(n, p) * n * n; }
+
+int launch_kinship(const double* G, int n, int64_t p, double* K, double* partial, cudaStream_t stream) {
+  const int ns = kinship_nsplit(n, p);
+  int64_t chunk = (p + ns - 1) / ns;
+  chunk = round_up(chunk, GK);
+  const int nsplit = (int)((p + chunk - 1) / chunk);
+  dim3 grid((n + GT - 1) / GT, (n + GT - 1) / GT, nsplit);
+  kinship_partial_kernel<<<grid, 256, 0, stream>>>(G, n, p, chunk, partial);
+  const int64_t nn = (int64_t)n * n;
+  kinship_finish_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, stream>>>(partial, nsplit, n, p, K);
+  return 2;
+}
+
+int launch_weight_consts(const double* h2_dev, int nk, const double* lambda, const double* C0, int n,
+                         int n_pad, int c, WeightConsts wc, int* flags, cudaStream_t stream) {
+  weight_consts_kernel<<<nk + 1, 128, 0, stream>>>(h2_dev, nk, lambda, C0, n, n_pad, c, wc, flags);
+  return 1;
+}
+
+int launch_trait_stats(const double* Y0, int64_t m, int n, int n_pad, int c, int nk, WeightConsts wc,
+                       LikParams lik, const double* grid_dev, double* Yr, double* ell, double* rss,
+                       int* best, double* ellmax, double* h2_out, int* bin_count, int* flags,
+                       cudaStream_t stream) {
+  const size_t smem = (size_t)WARPS_PER_BLOCK * n_pad * sizeof(double);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(trait_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const unsigned blocks = (unsigned)((m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  trait_stats_kernel<<<blocks, 32 * WARPS_PER_BLOCK, smem, stream>>>(Y0, m, n, n_pad, c, nk, wc, lik, grid_dev, Yr,
+                                                                      ell, rss, best, ellmax, h2_out, bin_count,
+                                                                      flags);
+  return 1;
+}
+
+int launch_marker_operand(const double* G0, int64_t p, int64_t p_pad, int n, int n_pad, int c, int nk,
+                          WeightConsts wc, double* Mop, int* flags, cudaStream_t stream) {
+  const size_t smem = (size_t)WARPS_PER_BLOCK * n_pad * sizeof(double);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(marker_operand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const unsigned blocks = (unsigned)((p_pad + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  marker_operand_kernel<<<blocks, 32 * WARPS_PER_BLOCK, smem, stream>>>(G0, p, p_pad, n, n_pad, c, nk, wc, Mop,
+                                                                         flags);
+  return 1;
+}
+
+int launch_alt_scalars(const double* ell, const double* rss, const double* ellmax, int64_t m,
+                       int64_t tcol_pad, int nk, int n, double* e, double* et, cudaStream_t stream) {
+  alt_scalars_kernel<<<(unsigned)((tcol_pad + 255) / 256), 256, 0, stream>>>(ell, rss, ellmax, m, tcol_pad, nk,
+                                                                              2.0 / (double)n, e, et);
+  return 1;
+}
+
+int launch_null_bins(const int* best, const double* rss, int64_t m, int nk, int tile, int64_t tcol_pad,
+                     int* bin_count, int* bin_start, int* bin_cursor, int* tile_k0, int* n_tiles,
+                     int* col_map, double* et, cudaStream_t stream) {
+  cudaMemsetAsync(col_map, 0xFF, (size_t)tcol_pad * sizeof(int), stream);
+  cudaMemsetAsync(et, 0, (size_t)tcol_pad * sizeof(double), stream);
+  bin_layout_kernel<<<1, 32, 0, stream>>>(bin_count, nk, tile, (int)(tcol_pad / tile), bin_start, bin_cursor,
+                                          tile_k0, n_tiles);
+  bin_scatter_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(best, rss, m, bin_start, bin_cursor, col_map,
+                                                                       et);
+  return 2;
+}
+
+int launch_pack_traits(const double* Yr, const int* col_map, int64_t m, int64_t tcol_pad, int n_pad,
+                       double* Top, cudaStream_t stream) {
+  const int64_t total = (int64_t)n_pad * tcol_pad;
+  pack_traits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(Yr, col_map, m, tcol_pad, n_pad, total,
+                                                                           Top);
+  return 1;
+}
+
+int launch_pack_perms(const double* z, const double* rss, const int32_t* perm_idx, int64_t nperms, int n,
+                      int n_pad, int64_t tcol_pad, double* Top, cudaStream_t stream) {
+  const int64_t total = (int64_t)n_pad * tcol_pad;
+  pack_perms_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(z, rss, perm_idx, nperms, n, tcol_pad,
+                                                                          total, Top);
+  return 1;
+}
+
+int launch_null_residual(const double* Yr, int n, int n_pad, int c, WeightConsts wc, double* z, double* rss,
+                         cudaStream_t stream) {
+  null_residual_kernel<<<1, 32, 0, stream>>>(Yr, n, n_pad, c, wc, z, rss);
+  return 1;
+}
+
+}  // namespace blmm

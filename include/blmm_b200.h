@@ -29,6 +29,12 @@ extern "C" {
 
 #define BLMM_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define BLMM_API __attribute__((visibility("default")))
+#else
+#define BLMM_API
+#endif
+
 /* status codes */
 enum {
   BLMM_OK = 0,
@@ -95,48 +101,54 @@ typedef struct {
 } blmm_opts;
 
 /* ---- context ------------------------------------------------------------------------------ */
-int blmm_abi_version(void);
-int blmm_create(blmm_ctx** out, int device);
-void blmm_destroy(blmm_ctx* ctx);
-const char* blmm_last_error(const blmm_ctx* ctx);
+BLMM_API int blmm_abi_version(void);
+BLMM_API int blmm_create(blmm_ctx** out, int device);
+BLMM_API void blmm_destroy(blmm_ctx* ctx);
+BLMM_API const char* blmm_last_error(const blmm_ctx* ctx);
 /* Wait for all work queued on the context's stream. */
-int blmm_sync(blmm_ctx* ctx);
+BLMM_API int blmm_sync(blmm_ctx* ctx);
 /* The context's CUDA stream as an opaque integer (cudaStream_t), for event timing by the host. */
-uint64_t blmm_stream(blmm_ctx* ctx);
+BLMM_API uint64_t blmm_stream(blmm_ctx* ctx);
 /* Number of kernels this library launched on the context since creation (bench's gpu_launches). */
-int64_t blmm_launch_count(const blmm_ctx* ctx);
+BLMM_API int64_t blmm_launch_count(const blmm_ctx* ctx);
+
+/* Optional device timing of the dominant kernel (the fused scan, blmm_scan.cu): when switched on,
+ * CUDA events are recorded on the context's stream around that launch; blmm_last_scan_ms() waits
+ * for the launch and returns its duration in milliseconds (-1 if none was timed).              */
+BLMM_API int blmm_set_profiling(blmm_ctx* ctx, int on);
+BLMM_API double blmm_last_scan_ms(blmm_ctx* ctx);
 
 /* ---- setup -------------------------------------------------------------------------------- */
 /* calcKinship(geno), src/kinship.jl:4-14.  G: n x p.  K_out: n x n. */
-int blmm_kinship(blmm_ctx* ctx, int64_t n, int64_t p, const double* G, double* K_out, int mem_space);
+BLMM_API int blmm_kinship(blmm_ctx* ctx, int64_t n, int64_t p, const double* G, double* K_out, int mem_space);
 
 /* The factorisation inside transform_rotation, src/transform_helpers.jl:21-49 (cuSOLVER syevd;
  * for a symmetric PSD K the SVD scheme is the same decomposition in descending order).
  * U_out: n x n (columns = eigenvectors), lambda_out: n (ascending for EIGEN, descending for SVD).
  * nneg_out (may be NULL): number of eigenvalues < -1e-7 (the reference warns, :27-30).          */
-int blmm_decompose(blmm_ctx* ctx, int64_t n, const double* K, int scheme, double* U_out,
+BLMM_API int blmm_decompose(blmm_ctx* ctx, int64_t n, const double* K, int scheme, double* U_out,
                    double* lambda_out, int* nneg_out, int mem_space);
 
 /* transform_rotation, src/transform_helpers.jl:1-54, given (U, lambda):
  * Y0_out = U'Y (n x m), X0_out = U'[Covar G] (n x (c+p)).  Either output may be NULL.          */
-int blmm_rotate(blmm_ctx* ctx, const blmm_problem* prob, double* Y0_out, double* X0_out, int mem_space);
+BLMM_API int blmm_rotate(blmm_ctx* ctx, const blmm_problem* prob, double* Y0_out, double* X0_out, int mem_space);
 
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* bulkscan(Y,G,Covar,K; method=...), src/bulkscan.jl:113-162.
  *   L_out : p x m LOD matrix (ld = opts->ld_out or p), marker index fastest.
  *   h2_out: m heritabilities (null-grid / null-exact: h2_null_list), or
  *           p x m h2_panel (alt-grid; may be NULL to skip the second output).                   */
-int blmm_bulkscan(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* L_out,
+BLMM_API int blmm_bulkscan(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* L_out,
                   double* h2_out);
 
 /* The |grid| x m matrix of null log-likelihoods `ell_results`, src/bulkscan_helpers.jl:267-269
  * (wls_multivar(...).Ell per grid point, src/wls.jl:103-176).  ell_out: ngrid x m, column-major. */
-int blmm_grid_loglik(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* ell_out);
+BLMM_API int blmm_grid_loglik(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* ell_out);
 
 /* fitlmm per trait, src/lmm.jl:56-86 (gridbrent src/gridbrent.jl:9-24 + Optim Brent), batched over
  * the m traits of `prob` (markers unused).  Outputs (each length m, any may be NULL):
  * h2_out, sigma2_out, ell_out.                                                                  */
-int blmm_fit_h2(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* h2_out,
+BLMM_API int blmm_fit_h2(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* h2_out,
                 double* sigma2_out, double* ell_out);
 
 /* scan(y,g,covar,K; permutation_test=true), src/scan.jl:485-557 (scan_perms_lite).  prob->m must
@@ -147,14 +159,14 @@ int blmm_fit_h2(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, 
  *   maxlod_out   : nperms       per-permutation max LOD (what get_thresholds consumes,
  *                               src/analysis_helpers/single_trait_analysis.jl:13-23), or NULL
  *   sigma2_out, h2_out : scalars (sigma2_e, h2_null)                                            */
-int blmm_scan_perms(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts,
+BLMM_API int blmm_scan_perms(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts,
                     const int32_t* perm_idx, int64_t nperms, double* lod_out, double* Lperms_out,
                     double* maxlod_out, double* sigma2_out, double* h2_out);
 
 /* scan(y,g,covar,K) null scan of single traits, src/scan.jl:310-360 (scan_null), evaluated in the
  * LiteQTL correlation form the reference's own tests equate it with (test/bulkscan_test.jl:60-80);
  * sqrt(w) without abs() as in scan_null.  lod_out: p x m, sigma2_out/h2_out: m.     */
-int blmm_scan_null(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* lod_out,
+BLMM_API int blmm_scan_null(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* lod_out,
                    double* sigma2_out, double* h2_out);
 
 #ifdef __cplusplus
