@@ -5,6 +5,7 @@
 #include <cusolverDn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -20,7 +21,7 @@ using namespace blmm;
 enum Slot {
   S_Y_IN, S_G_IN, S_C_IN, S_U_IN, S_LAM, S_GRID, S_Y0, S_C0, S_G0, S_YR, S_W, S_SW, S_Q, S_SLW, S_LDS,
   S_ELL, S_RSS, S_BEST, S_ELLMAX, S_MOP, S_TOP, S_E, S_ET, S_BINS, S_TILEK0, S_COLMAP, S_L, S_H2P, S_H2V,
-  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_COUNT
+  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_LOGTAB, S_COUNT
 };
 
 struct blmm_ctx {
@@ -171,7 +172,12 @@ void copy_out(blmm_ctx* ctx, double* dst, const double* src_dev, size_t count, i
                            ctx->stream));
 }
 
-void run_scan(blmm_ctx* ctx, const ScanParams& P) {
+void run_scan(blmm_ctx* ctx, ScanParams P) {
+  if (!ctx->buf[S_LOGTAB]) {
+    double* tab = ws<double>(ctx, S_LOGTAB, scan_logtab_doubles());
+    ctx->launches += launch_logtab(tab, ctx->stream);
+  }
+  P.logtab = reinterpret_cast<const double*>(ctx->buf[S_LOGTAB]);
   if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   ctx->launches += launch_scan(P, ctx->sm_count, ctx->stream);
   if (ctx->profiling) {
@@ -228,6 +234,7 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   ScanParams P{};
   P.Mop = Mop;
   P.grid = d_grid;
+  P.ngrid = nk;
   P.nq = R.nq;
   P.p = (int)p;
   P.p_pad = (int)p_pad;
@@ -397,11 +404,13 @@ int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const 
     }
   }
   double* Top = ws<double>(ctx, S_TOP, (size_t)R.n_pad * tcol_pad);
-  ctx->launches += launch_pack_perms(z, zrss, d_perm, nperms, R.n, R.n_pad, tcol_pad, Top, ctx->stream);
+  double* et1 = ws<double>(ctx, S_ET, tcol_pad);
+  ctx->launches += launch_pack_perms(z, zrss, d_perm, nperms, R.n, R.n_pad, tcol_pad, Top, et1, ctx->stream);
 
   ScanParams P{};
   P.Top = Top;
   P.Mop = Mop;
+  P.et = et1;
   P.nq = R.nq;
   P.p = (int)p;
   P.p_pad = (int)p_pad;

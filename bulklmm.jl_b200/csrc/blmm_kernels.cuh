@@ -79,8 +79,9 @@ int launch_pack_traits(const double* Yr, const int* col_map, int64_t m, int64_t 
 // Permutation operand (transform_permute + column normalisation, src/transform_helpers.jl:94-102,
 // src/scan.jl:531-536): column 0 = z/||z||, column s>=1 = z[perm_idx[:,s-1]]/||z||, where z is the
 // weighted null residual (padded column 0 of Zr) and rss = ||z||^2.
+// Also fills et[0..tcol_pad) with 1 (the columns are already normalised).
 int launch_pack_perms(const double* z, const double* rss, const int32_t* perm_idx, int64_t nperms, int n,
-                      int n_pad, int64_t tcol_pad, double* Top, cudaStream_t stream);
+                      int n_pad, int64_t tcol_pad, double* Top, double* et, cudaStream_t stream);
 
 // z = P (sw .* y): the re-weighted null residual `copy_r0` of transform_reweight
 // (src/transform_helpers.jl:71-82) for one trait, weight slot 0 of wc.  Writes z (n_pad) and rss.
@@ -107,11 +108,13 @@ struct ScanParams {
   const double* Top;       // trait operand   [nq][tcol_pad][KC]
   const double* Mop;       // marker operand  [nk_total][nq][p_pad][KC]
   const double* e;         // [nk][tcol_pad] or nullptr (=> 1)
-  const double* et;        // [nk][tcol_pad] or nullptr (=> 1)
+  const double* et;        // [nk][tcol_pad], required
   const int* tile_k0;      // per trait tile: first k (index into Mop); nullptr => 0
   const int* n_tiles_dev;  // device scalar: number of trait tiles in use; nullptr => n_tiles_t
   const int* col_map;      // [tcol_pad] packed column -> output column (-1 = padding); nullptr => identity
-  const double* grid;      // device copy of the h2 grid (for the h2 panel)
+  const double* grid;      // device copy of the h2 grid (for the h2 panel), ngrid <= 255 values
+  const double* logtab;    // log10 table of the final epilogue (launch_logtab)
+  int ngrid;
   double* L;               // p x m output, ld = ldL (nullptr => not stored)
   double* L0;              // if non-null: output column 0 goes here (length p) and column s >= 1 goes to
                            // column s-1 of L / colmax (scan_perms_lite's lod vs L_perms split, src/scan.jl:545-546)
@@ -133,6 +136,9 @@ constexpr int SCAN_TT = 128;  // traits per CTA tile
 constexpr int SCAN_MT = 64;   // markers per CTA tile
 // Largest number of K-chunks the shared-memory-resident kernel supports for a k-list of nk.
 int scan_max_nq(int nk);
+// the 128-entry {1/c, -log10(1/c)} table used by the kernel's logarithm; built once per context
+int scan_logtab_doubles();
+int launch_logtab(double* tab, cudaStream_t stream);
 int launch_scan(const ScanParams& P, int sm_count, cudaStream_t stream);
 
 }  // namespace blmm

@@ -433,7 +433,7 @@ __global__ void pack_traits_kernel(const double* __restrict__ Yr, const int* __r
 
 __global__ void pack_perms_kernel(const double* __restrict__ z, const double* __restrict__ rss,
                                   const int32_t* __restrict__ perm_idx, int64_t nperms, int n, int64_t tcol_pad,
-                                  int64_t total, double* __restrict__ Top) {
+                                  int64_t total, double* __restrict__ Top, double* __restrict__ et) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int kk = (int)(idx % KC);
@@ -446,6 +446,7 @@ __global__ void pack_perms_kernel(const double* __restrict__ z, const double* __
     v = z[src] / sqrt(*rss);
   }
   Top[idx] = v;
+  if (q == 0 && kk == 0) et[s] = 1.0;
 }
 
 __global__ void __launch_bounds__(32) null_residual_kernel(const double* __restrict__ Yr, int n, int n_pad, int c,
@@ -551,10 +552,10 @@ int launch_pack_traits(const double* Yr, const int* col_map, int64_t m, int64_t 
 }
 
 int launch_pack_perms(const double* z, const double* rss, const int32_t* perm_idx, int64_t nperms, int n,
-                      int n_pad, int64_t tcol_pad, double* Top, cudaStream_t stream) {
+                      int n_pad, int64_t tcol_pad, double* Top, double* et, cudaStream_t stream) {
   const int64_t total = (int64_t)n_pad * tcol_pad;
   pack_perms_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(z, rss, perm_idx, nperms, n, tcol_pad,
-                                                                          total, Top);
+                                                                          total, Top, et);
   return 1;
 }
 

@@ -1,14 +1,16 @@
 // The fused marker x trait scan kernel (see ScanParams in blmm_kernels.cuh for the arithmetic).
 //
-// Structure (sm_100a): persistent CTAs, one per SM.  A CTA owns a contiguous range of
-// (trait tile, marker tile) units.  The trait tile (128 traits x whole K) stays resident in shared
-// memory; for every unit the k-list's marker tiles (64 markers x whole K, plus that k's per-trait
-// scalars e/et) stream through a 2-3 stage ring filled by one producer warp with 1-D bulk
-// asynchronous copies (cp.async.bulk -> UBLKCP, the TMA engine; mbarrier transaction counts).
-// Eight consumer warps each own a 32 marker x 32 trait block: FP64 tensor-core mma.sync m8n8k4
-// (DMMA.8x8x4) over the K-chunked operands, then the per-k epilogue in registers
-// (v = e - d^2*et, running min, tmax! counter), and ONE log10 per output after the last k.
-// LOD / h2 panels are written once with streaming stores; nothing per-grid-point touches HBM.
+// Structure (sm_100a): persistent CTAs, one per SM, 8 warps (2 per SM sub-partition, so every
+// thread may hold up to 255 registers: accumulators + running minima + counters + double-buffered
+// fragments stay in registers).  A CTA owns a contiguous range of (trait tile, marker tile) units.
+// The trait tile (128 traits x whole K) stays resident in shared memory; for every unit the
+// k-list's marker tiles (64 markers x whole K, plus that k's per-trait scalars e/et) stream
+// through a 2-3 stage ring filled with 1-D bulk asynchronous copies (cp.async.bulk -> UBLKCP, the
+// TMA engine; mbarrier transaction counts), issued by one elected thread NS-1 iterations ahead.
+// Each warp owns a 32 marker x 32 trait block: FP64 tensor-core mma.sync m8n8k4 (DMMA.8x8x4)
+// over the K-chunked operands, then the per-k epilogue in registers (v = e - d^2*et, running
+// min, tmax! counter), and ONE logarithm per output after the last k.  LOD / h2 panels are
+// written once with streaming stores; nothing per-grid-point touches HBM.
 #include <math.h>
 
 #include "blmm_kernels.cuh"
@@ -19,9 +21,12 @@ namespace {
 
 constexpr int TT = SCAN_TT;  // traits per CTA tile
 constexpr int MT = SCAN_MT;  // markers per CTA tile
-constexpr int CONSUMER_WARPS = 8;
-constexpr int SCAN_THREADS = 32 * (CONSUMER_WARPS + 1);
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int LOGTAB_N = 128;
+#ifndef BLMM_SCAN_BT
+#define BLMM_SCAN_BT 2
+#endif
+constexpr int GRID_MAX = 256;
 
 struct SmemPlan {
   int nstage;
@@ -30,184 +35,265 @@ struct SmemPlan {
   size_t bytes;
 };
 
+constexpr size_t FIXED_SMEM = (size_t)LOGTAB_N * 16 + GRID_MAX * 8 + 128;
+
 __host__ __device__ inline SmemPlan plan_smem(int nq) {
   SmemPlan s;
   s.top_doubles = (size_t)nq * TT * KC;
   s.stage_doubles = (size_t)nq * MT * KC + 2 * TT;
   s.nstage = 3;
-  s.bytes = (s.top_doubles + 3 * s.stage_doubles) * 8 + 64;
+  s.bytes = (s.top_doubles + 3 * s.stage_doubles) * 8 + FIXED_SMEM;
   if (s.bytes > SMEM_LIMIT) {
     s.nstage = 2;
-    s.bytes = (s.top_doubles + 2 * s.stage_doubles) * 8 + 64;
+    s.bytes = (s.top_doubles + 2 * s.stage_doubles) * 8 + FIXED_SMEM;
   }
   return s;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanParams P) {
+// ---------------------------------------------------------------------------------------------
+// log10 for the final epilogue.  The FP64 pipe is shared by DMMA and scalar double arithmetic on
+// B200 (profiles/fp64_peak_r01.json: mixed loop), so the logarithm is kept to ~12 FP64
+// operations: v = 2^e * m, m in [0.75, 1.5); a 128-entry table gives rcp ~ 1/c and -log10(rcp)
+// for the interval of m; r = m*rcp - 1 (|r| <= 2^-7); log1p(r) by an 8-term series.  The two
+// intervals touching 1 use rcp = 1 exactly, so results keep full relative accuracy as v -> 1
+// (LOD -> 0).  Absolute error ~1e-16, far inside the 1e-8 parity tolerance.
+// `special` is raised for operands outside the positive normal range (fixed up by the caller).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_log10(double v, const double2* __restrict__ tab, bool& special) {
+  const int hi = __double2hiint(v), lo = __double2loint(v);
+  const int ix = hi - 0x3fe80000;
+  const int e = ix >> 20;
+  const double m = __hiloint2double(hi - (e << 20), lo);
+  const double2 t = tab[(ix >> 13) & (LOGTAB_N - 1)];
+  const double r = fma(m, t.x, -1.0);
+  double q = fma(r, -1.0 / 8.0, 1.0 / 7.0);
+  q = fma(q, r, -1.0 / 6.0);
+  q = fma(q, r, 1.0 / 5.0);
+  q = fma(q, r, -1.0 / 4.0);
+  q = fma(q, r, 1.0 / 3.0);
+  q = fma(q, r, -1.0 / 2.0);
+  q = fma(q, r, 1.0);
+  const double lp = q * r;
+  special |= (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
+  return fma(lp, 0.43429448190325182765, fma((double)e, 0.30102999566398119521, t.y));
+}
+
+// IEEE results for the operands fast_log10 flags: v = 0 (r^2 = 1) -> -inf as log10 (a subnormal
+// v, unreachable as 1 - r^2, is treated as 0); v < 0 -> NaN (Julia's log10 throws there);
+// inf / NaN pass through.
+__device__ __forceinline__ double fix_log10(double v, double res) {
+  const int hi = __double2hiint(v);
+  res = ((unsigned)hi < 0x00100000u) ? -INFINITY : res;
+  res = (hi < 0) ? __longlong_as_double(0x7ff8000000000000LL) : res;
+  res = (hi >= 0x7ff00000) ? v : res;
+  return res;
+}
+
+// first k-step of a tile: C = 0 (no separate zeroing of the accumulators)
+__device__ __forceinline__ void dmma884_zero(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};"
+      : "=d"(c0), "=d"(c1)
+      : "d"(a), "d"(b), "d"(0.0));
+}
+
+// BT = 8-trait atoms per warp: BT = 4 -> 8 warps of 32 markers x 32 traits, BT = 2 -> 16 warps of
+// 32 markers x 16 traits (4 warps per SM sub-partition, <= 128 registers per thread).
+template <int NQ, bool ARGMAX, int BT, bool HAS_E>
+__global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const ScanParams P) {
+  constexpr int WT_WARPS = TT / (8 * BT);  // warps along the trait dimension
+  constexpr int NWARPS = 2 * WT_WARPS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int nq = P.nq;
-  const SmemPlan plan = plan_smem(nq);
+  const SmemPlan plan = plan_smem(NQ);
   const int NS = plan.nstage;
   double* top = reinterpret_cast<double*>(smem_raw);
   double* stages = top + plan.top_doubles;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stages + NS * plan.stage_doubles);
-  uint64_t* full = bars;           // [NS]
-  uint64_t* empty = bars + 3;      // [NS]
-  uint64_t* top_full = bars + 6;
-  uint64_t* top_empty = bars + 7;
+  double2* logtab = reinterpret_cast<double2*>(stages + NS * plan.stage_doubles);
+  double* grid_s = reinterpret_cast<double*>(logtab + LOGTAB_N);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(grid_s + GRID_MAX);
+  uint64_t* full = bars;  // [NS]
+  uint64_t* top_full = bars + 3;
+  uint64_t* top_empty = bars + 4;
+  int* rel_cnt = reinterpret_cast<int*>(bars + 5);  // [NS] consumers done with a stage
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CONSUMER_WARPS);
+      rel_cnt[s] = 0;
     }
     mbar_init(top_full, 1);
-    mbar_init(top_empty, CONSUMER_WARPS);
+    mbar_init(top_empty, NWARPS);
     mbar_fence_init();
   }
+  if (tid < LOGTAB_N) logtab[tid] = reinterpret_cast<const double2*>(P.logtab)[tid];
+  if (P.grid && tid < P.ngrid) grid_s[tid] = P.grid[tid];
   __syncthreads();
 
   const int n_tiles = P.n_tiles_dev ? *P.n_tiles_dev : P.n_tiles_t;
   const int n_mt = P.p_pad / MT;
-  const int64_t units = (int64_t)n_tiles * n_mt;
-  const int64_t u0 = units * blockIdx.x / gridDim.x;
-  const int64_t u1 = units * (blockIdx.x + 1) / gridDim.x;
+  const int64_t units = (int64_t)n_tiles * n_mt;  // < 2^31 (checked by the launcher)
+  const int u0 = (int)(units * blockIdx.x / gridDim.x);
+  const int u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
   const int nk = P.nk;
-  const uint32_t marker_chunk_bytes = MT * KC * 8;
-  const uint32_t trait_chunk_bytes = TT * KC * 8;
+  const int total_it = (u1 - u0) * nk;
+  constexpr uint32_t marker_chunk_bytes = MT * KC * 8;
+  constexpr uint32_t trait_chunk_bytes = TT * KC * 8;
+  constexpr uint32_t stage_bytes = (uint32_t)NQ * marker_chunk_bytes + TT * 8 + (HAS_E ? TT * 8 : 0);
 
-  if (warp == CONSUMER_WARPS) {
-    // ------------------------------- producer ------------------------------------------------
-    if (lane == 0) {
-      int64_t it = 0;
-      int ntop = 0, cur_tt = -1;
-      for (int64_t u = u0; u < u1; ++u) {
-        const int tt = (int)(u / n_mt), mt = (int)(u % n_mt);
-        if (tt != cur_tt) {
-          if (ntop > 0) mbar_wait(top_empty, (ntop - 1) & 1);
-          mbar_arrive_expect_tx(top_full, (uint32_t)nq * trait_chunk_bytes);
-          for (int q = 0; q < nq; ++q)
-            bulk_g2s(top + (size_t)q * TT * KC, P.Top + ((size_t)q * P.tcol_pad + (size_t)tt * TT) * KC,
-                     trait_chunk_bytes, top_full);
-          ++ntop;
-          cur_tt = tt;
-        }
-        const int k0 = P.tile_k0 ? P.tile_k0[tt] : 0;
-        for (int kk = 0; kk < nk; ++kk, ++it) {
-          const int s = (int)(it % NS);
-          if (it >= NS) mbar_wait(&empty[s], (uint32_t)((it / NS) - 1) & 1);
-          double* st = stages + (size_t)s * plan.stage_doubles;
-          uint32_t bytes = (uint32_t)nq * marker_chunk_bytes;
-          if (P.e) bytes += TT * 8;
-          if (P.et) bytes += TT * 8;
-          mbar_arrive_expect_tx(&full[s], bytes);
-          const double* src = P.Mop + (((size_t)(k0 + kk) * nq) * P.p_pad + (size_t)mt * MT) * KC;
-          for (int q = 0; q < nq; ++q)
-            bulk_g2s(st + (size_t)q * MT * KC, src + (size_t)q * P.p_pad * KC, marker_chunk_bytes, &full[s]);
-          double* sc = st + (size_t)nq * MT * KC;
-          if (P.e) bulk_g2s(sc, P.e + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
-          if (P.et) bulk_g2s(sc + TT, P.et + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
-        }
+  // Fill stage s with the operands of iteration (tt, mt, kk): the k-th marker tile and that k's
+  // per-trait scalars.  Called by one thread; completion is counted on full[s].
+  auto issue_stage = [&](int s, int tt, int mt, int kk) {
+    const int k0 = P.tile_k0 ? P.tile_k0[tt] : 0;
+    double* st = stages + (size_t)s * plan.stage_doubles;
+    mbar_arrive_expect_tx(&full[s], stage_bytes);
+    const double* src = P.Mop + (((size_t)(k0 + kk) * NQ) * P.p_pad + (size_t)mt * MT) * KC;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      bulk_g2s(st + (size_t)q * MT * KC, src + (size_t)q * P.p_pad * KC, marker_chunk_bytes, &full[s]);
+    double* sc = st + (size_t)NQ * MT * KC;
+    bulk_g2s(sc + TT, P.et + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
+    if (HAS_E) bulk_g2s(sc, P.e + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
+  };
+  // (tt, mt, kk) advanced by `steps` iterations
+  auto advance = [&](int& tt, int& mt, int& kk, int steps) {
+    kk += steps;
+    while (kk >= nk) {
+      kk -= nk;
+      if (++mt == n_mt) {
+        mt = 0;
+        ++tt;
       }
     }
-    return;
+  };
+
+  int tt = u0 / n_mt, mt = u0 % n_mt;
+  if (tid == 0) {
+    int ptt = tt, pmt = mt, pkk = 0;
+    for (int i = 0; i < NS && i < total_it; ++i) {
+      issue_stage(i, ptt, pmt, pkk);
+      advance(ptt, pmt, pkk, 1);
+    }
   }
 
-  // --------------------------------- consumers -------------------------------------------------
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp >> 2;  // marker sub-block (0..1)
-  const int wt = warp & 3;   // trait sub-block (0..3)
+  const int wm = warp / WT_WARPS;  // marker sub-block (0..1)
+  const int wt = warp % WT_WARPS;  // trait sub-block
   const int aoff = (wm * 32 + g) * KC + t;
-  const int boff = (wt * 32 + g) * KC + t;
-  const bool has_e = P.e != nullptr, has_et = P.et != nullptr;
+  const int boff = (wt * (8 * BT) + g) * KC + t;
 
-  int64_t it = 0;
+  int it = 0, s = 0;
+  uint32_t sphase = 0;  // parity of the ring round
   int ntop = 0, cur_tt = -1;
-  for (int64_t u = u0; u < u1; ++u) {
-    const int tt = (int)(u / n_mt), mt = (int)(u % n_mt);
+  for (int u = u0; u < u1; ++u) {
     if (tt != cur_tt) {
+      if (tid == 0) {
+        if (ntop > 0) mbar_wait(top_empty, (ntop - 1) & 1);
+        mbar_arrive_expect_tx(top_full, (uint32_t)NQ * trait_chunk_bytes);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+          bulk_g2s(top + (size_t)q * TT * KC, P.Top + ((size_t)q * P.tcol_pad + (size_t)tt * TT) * KC,
+                   trait_chunk_bytes, top_full);
+      }
       mbar_wait(top_full, ntop & 1);
       ++ntop;
       cur_tt = tt;
     }
-    const bool last_of_tt = (u + 1 == u1) || ((int)((u + 1) / n_mt) != tt);
+    const bool last_of_tt = (u + 1 == u1) || (mt + 1 == n_mt);
 
-    double acc[4][4][2];
-    double vmin[4][4][2];
-    uint32_t cnt[8];
+    double acc[4][BT][2];
+    double vmin[4][BT][2];
+    uint32_t cnt[2 * BT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cnt[i] = 0u;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        acc[a][b][0] = acc[a][b][1] = 0.0;
-        vmin[a][b][0] = vmin[a][b][1] = 0.0;
-      }
+    for (int i = 0; i < 2 * BT; ++i) cnt[i] = 0u;
 
     for (int kk = 0; kk < nk; ++kk, ++it) {
-      const int s = (int)(it % NS);
-      mbar_wait(&full[s], (uint32_t)(it / NS) & 1);
+      mbar_wait(&full[s], sphase);
       const double* ms = stages + (size_t)s * plan.stage_doubles;
-      for (int q = 0; q < nq; ++q) {
-        const double* ap = ms + q * (MT * KC) + aoff;
-        const double* bp = top + q * (TT * KC) + boff;
+      {
+        // K loop, fully unrolled, fragments double-buffered in registers
+        const double* ap = ms + aoff;
+        const double* bp = top + boff;
+        double af[2][4], bf[2][BT];
 #pragma unroll
-        for (int st = 0; st < KC / 4; ++st) {
-          double af[4], bf[4];
+        for (int a = 0; a < 4; ++a) af[0][a] = ap[a * 8 * KC];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) af[a] = ap[a * 8 * KC + st * 4];
+        for (int b = 0; b < BT; ++b) bf[0][b] = bp[b * 8 * KC];
 #pragma unroll
-          for (int b = 0; b < 4; ++b) bf[b] = bp[b * 8 * KC + st * 4];
+        for (int st = 0; st < NQ * (KC / 4); ++st) {
+          const int cur = st & 1;
+          if (st + 1 < NQ * (KC / 4)) {
+            const int q1 = (st + 1) / (KC / 4), s1 = (st + 1) % (KC / 4);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[cur ^ 1][a] = ap[q1 * (MT * KC) + a * 8 * KC + s1 * 4];
+#pragma unroll
+            for (int b = 0; b < BT; ++b) bf[cur ^ 1][b] = bp[q1 * (TT * KC) + b * 8 * KC + s1 * 4];
+          }
 #pragma unroll
           for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            for (int b = 0; b < BT; ++b) {
+              if (st == 0)
+                dmma884_zero(acc[a][b][0], acc[a][b][1], af[cur][a], bf[cur][b]);
+              else
+                dmma884(acc[a][b][0], acc[a][b][1], af[cur][a], bf[cur][b]);
+            }
         }
       }
-      // per-k trait scalars for this lane's 8 trait columns
-      double ek[4][2], etk[4][2];
+      // per-k trait scalars for this lane's 2*BT trait columns
+      double ek[BT][2], etk[BT][2];
       {
-        const double* sc = ms + (size_t)nq * MT * KC + wt * 32 + 2 * t;
+        const double* sc = ms + (size_t)NQ * MT * KC + wt * (8 * BT) + 2 * t;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (has_e) {
+        for (int b = 0; b < BT; ++b) {
+          if (HAS_E) {
             const double2 v = *reinterpret_cast<const double2*>(sc + b * 8);
             ek[b][0] = v.x; ek[b][1] = v.y;
           } else {
             ek[b][0] = ek[b][1] = 1.0;
           }
-          if (has_et) {
-            const double2 v = *reinterpret_cast<const double2*>(sc + TT + b * 8);
-            etk[b][0] = v.x; etk[b][1] = v.y;
-          } else {
-            etk[b][0] = etk[b][1] = 1.0;
+          const double2 w = *reinterpret_cast<const double2*>(sc + TT + b * 8);
+          etk[b][0] = w.x; etk[b][1] = w.y;
+        }
+      }
+      // Release the stage.  The last of the NWARPS consumers refills it at once with the operands
+      // of iteration it + NS, so the copy is in flight as early as the ring allows.
+      __syncwarp();
+      if (lane == 0) {
+        if (last_of_tt && kk == nk - 1) mbar_arrive(top_empty);
+        __threadfence_block();
+        if (atomicAdd(&rel_cnt[s], 1) == NWARPS - 1) {
+          rel_cnt[s] = 0;
+          if (it + NS < total_it) {
+            int ntt = tt, nmt = mt, nkk = kk;
+            advance(ntt, nmt, nkk, NS);
+            issue_stage(s, ntt, nmt, nkk);
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&empty[s]);
-        if (last_of_tt && kk == nk - 1) mbar_arrive(top_empty);
+      if (++s == NS) {
+        s = 0;
+        sphase ^= 1u;
       }
+
       const bool first = (kk == 0);
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
+        for (int b = 0; b < BT; ++b)
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const double d = acc[a][b][cc];
             const double v = fma(-(d * d), etk[b][cc], ek[b][cc]);
-            acc[a][b][cc] = 0.0;
-            const bool better = v < vmin[a][b][cc];  // strict, as `max .< to_compare` in tmax!
+            // strict `<` as `max .< to_compare` in tmax!, on the bit patterns (integer pipe; the
+            // FP64 pipe is the bottleneck).  Equivalent for the non-negative v that occur; a
+            // negative v (r^2 > 1 by rounding) orders below every positive one, as it should.
+            const bool better = __double_as_longlong(v) < __double_as_longlong(vmin[a][b][cc]);
             const bool upd = first || better;
             vmin[a][b][cc] = upd ? v : vmin[a][b][cc];
-            const int o = (a * 4 + b) * 2 + cc;
+            const int o = (a * BT + b) * 2 + cc;
             const int sh = (o & 3) * 8;
-            if (P.argmax_mode) {
+            if (ARGMAX) {
               if (upd) cnt[o >> 2] = (cnt[o >> 2] & ~(0xFFu << sh)) | ((uint32_t)kk << sh);
             } else {
               if (better && !first) cnt[o >> 2] += (1u << sh);
@@ -216,14 +302,30 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanParams 
     }
 
     // final epilogue: one logarithm per output, streaming stores
+    bool special = false;
+    double lod[4][BT][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) lod[a][b][cc] = fast_log10(vmin[a][b][cc], logtab, special);
+    if (__any_sync(0xffffffffu, special)) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) lod[a][b][cc] = fix_log10(vmin[a][b][cc], lod[a][b][cc]);
+    }
     const int k0 = P.tile_k0 ? P.tile_k0[tt] : 0;
-    const int kbase = P.argmax_mode ? k0 : 0;
+    const int kbase = ARGMAX ? k0 : 0;
     const int i_base = mt * MT + wm * 32 + g;
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+    for (int b = 0; b < BT; ++b)
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
-        const int64_t pos = (int64_t)tt * TT + wt * 32 + b * 8 + 2 * t + cc;
+        const int64_t pos = (int64_t)tt * TT + wt * (8 * BT) + b * 8 + 2 * t + cc;
         const int64_t col = P.col_map ? (int64_t)P.col_map[pos] : (pos < P.m ? pos : -1);
         // output column pointers (column 0 may be split off, see ScanParams::L0)
         double* Lc = nullptr;
@@ -247,15 +349,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanParams 
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
           const int i = i_base + a * 8;
-          const double lod = -P.half_n * log10(vmin[a][b][cc]);
+          const double l = -P.half_n * lod[a][b][cc];
           if (i < P.p) {
-            if (Lc) st_stream(Lc + i, lod);
+            if (Lc) st_stream(Lc + i, l);
             if (Hc) {
-              const int o = (a * 4 + b) * 2 + cc;
+              const int o = (a * BT + b) * 2 + cc;
               const int cv = (int)((cnt[o >> 2] >> ((o & 3) * 8)) & 0xFFu);
-              st_stream(Hc + i, P.grid[kbase + cv]);
+              st_stream(Hc + i, grid_s[kbase + cv]);
             }
-            cmax = fmax(cmax, lod);
+            cmax = fmax(cmax, l);
           }
         }
         if (P.colmax) {
@@ -265,6 +367,48 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanParams 
           if (g == 0 && Mc) atomic_max_nonneg(Mc, cmax + 0.0);
         }
       }
+    if (++mt == n_mt) {
+      mt = 0;
+      ++tt;
+    }
+  }
+}
+
+__global__ void logtab_kernel(double* tab) {
+  const int i = threadIdx.x;
+  if (i >= LOGTAB_N) return;
+  double c;
+  if (i == 63 || i == 64)
+    c = 1.0;
+  else if (i < 64)
+    c = 0.75 + ((double)i + 0.5) / 256.0;
+  else
+    c = 1.0 + ((double)(i - 64) + 0.5) / 128.0;
+  const double rcp = 1.0 / c;
+  tab[2 * i] = rcp;
+  tab[2 * i + 1] = (rcp == 1.0) ? 0.0 : -log10(rcp);
+}
+
+constexpr int SCAN_BT = BLMM_SCAN_BT;
+
+template <int NQ, bool ARGMAX, bool HAS_E>
+void launch_one(const ScanParams& P, int sm_count, cudaStream_t stream) {
+  const SmemPlan plan = plan_smem(NQ);
+  constexpr int threads = 32 * 2 * (TT / (8 * SCAN_BT));
+  cudaFuncSetAttribute(scan_kernel<NQ, ARGMAX, SCAN_BT, HAS_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  scan_kernel<NQ, ARGMAX, SCAN_BT, HAS_E><<<sm_count, threads, plan.bytes, stream>>>(P);
+}
+
+template <int NQ>
+void launch_nq(const ScanParams& P, int sm_count, cudaStream_t stream) {
+  if (P.e) {
+    if (P.argmax_mode)
+      launch_one<NQ, true, true>(P, sm_count, stream);
+    else
+      launch_one<NQ, false, true>(P, sm_count, stream);
+  } else {
+    // one-element k-lists (null-grid bins, permutations): the h2 panel is not produced
+    launch_one<NQ, false, false>(P, sm_count, stream);
   }
 }
 
@@ -272,15 +416,25 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const ScanParams 
 
 int scan_max_nq(int nk) {
   (void)nk;
-  int nq = 1;
-  while (plan_smem(nq + 1).bytes <= (size_t)SMEM_LIMIT) ++nq;
-  return nq;
+  return 5;
+}
+
+int scan_logtab_doubles() { return 2 * LOGTAB_N; }
+
+int launch_logtab(double* tab, cudaStream_t stream) {
+  logtab_kernel<<<1, LOGTAB_N, 0, stream>>>(tab);
+  return 1;
 }
 
 int launch_scan(const ScanParams& P, int sm_count, cudaStream_t stream) {
-  const SmemPlan plan = plan_smem(P.nq);
-  cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  scan_kernel<<<sm_count, SCAN_THREADS, plan.bytes, stream>>>(P);
+  switch (P.nq) {
+    case 1: launch_nq<1>(P, sm_count, stream); break;
+    case 2: launch_nq<2>(P, sm_count, stream); break;
+    case 3: launch_nq<3>(P, sm_count, stream); break;
+    case 4: launch_nq<4>(P, sm_count, stream); break;
+    case 5: launch_nq<5>(P, sm_count, stream); break;
+    default: return 0;
+  }
   return 1;
 }
 

@@ -71,6 +71,46 @@ __global__ void mixed_kernel(double* out, int iters, double a0, double b0) {
   if (s == 12345.678) out[0] = s;
 }
 
+// realistic inner loop: 4x4 (or 4x2) atoms per warp, fragments re-loaded from shared memory every k-step
+// with the scan kernel's [row][KC=20] layout; no epilogue, no barriers.
+template <int BT>
+__global__ void dmma_tile_kernel(double* out, int iters) {
+  __shared__ double sa[64 * 20], sb[128 * 20];
+  for (int i = threadIdx.x; i < 64 * 20; i += blockDim.x) sa[i] = 1e-3 * i;
+  for (int i = threadIdx.x; i < 128 * 20; i += blockDim.x) sb[i] = 1e-4 * i;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const double* ap = sa + ((warp & 1) * 32 + g) * 20 + t;
+  const double* bp = sb + (((warp >> 1) * 8 * BT) % 128 + g) * 20 + t;
+  double c[4][BT][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < BT; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+      double af[4], bf[BT];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) af[a] = ap[a * 160 + st * 4];
+#pragma unroll
+      for (int b = 0; b < BT; ++b) bf[b] = bp[b * 160 + st * 4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+          asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+              : "+d"(c[a][b][0]), "+d"(c[a][b][1]) : "d"(af[a]), "d"(bf[b]));
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < BT; ++b) s += c[a][b][0] + c[a][b][1];
+  if (s == 12345.678) out[0] = s;
+}
+
 template <typename F>
 float time_ms(F&& launch, int reps = 5) {
   cudaEvent_t e0, e1;
@@ -108,6 +148,15 @@ int main() {
   {
     float ms = time_ms([&] { dmma_kernel<16><<<sms, 8 * 32>>>(out, iters, 1.0, 1e-3); });
     printf(", \"dmma_tflops_w8_acc16\": %.3f", (double)sms * 8 * iters * 16 * 512.0 / (ms * 1e-3) / 1e12);
+  }
+  {
+    const int it2 = 4000;
+    float ms = time_ms([&] { dmma_tile_kernel<4><<<sms, 8 * 32>>>(out, it2); });
+    printf(", \"dmma_tile_4x4_w8_tflops\": %.3f", (double)sms * 8 * it2 * 5 * 16 * 512.0 / (ms * 1e-3) / 1e12);
+    ms = time_ms([&] { dmma_tile_kernel<2><<<sms, 16 * 32>>>(out, it2); });
+    printf(", \"dmma_tile_4x2_w16_tflops\": %.3f", (double)sms * 16 * it2 * 5 * 8 * 512.0 / (ms * 1e-3) / 1e12);
+    ms = time_ms([&] { dmma_tile_kernel<4><<<sms, 4 * 32>>>(out, it2); });
+    printf(", \"dmma_tile_4x4_w4_tflops\": %.3f", (double)sms * 4 * it2 * 5 * 16 * 512.0 / (ms * 1e-3) / 1e12);
   }
   // (b) DFMA: 32 FMA = 64 flop per warp instruction
   for (int warps : {8, 16, 32}) {
