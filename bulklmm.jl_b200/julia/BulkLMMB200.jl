@@ -1,0 +1,243 @@
+# BulkLMMB200.jl — Julia shim over libblmm_b200.so (include/blmm_b200.h).
+#
+# Keeps the reference's public API for the multi-trait genome-scan path and replaces the bodies by
+# `ccall`s into the sm_100a CUDA library:
+#
+#     bulkscan(Y, G, K; ...), bulkscan(Y, G, Covar, K; ...)          src/bulkscan.jl:81-162
+#     bulkscan_null / bulkscan_null_grid / bulkscan_alt_grid         src/bulkscan.jl:188-526
+#     scan(y, g, K; permutation_test = true, nperms, rndseed, ...)   src/scan.jl:94-271, 485-557
+#     calcKinship(geno)                                              src/kinship.jl:4-14
+#     transform_rotation(y, g, K; ...)                               src/transform_helpers.jl:1-54
+#
+# STATUS: Julia is not installed in the build image, so this file has been written against the C header
+# but NOT executed there.  The same ABI is exercised end to end from Python ctypes
+# (bulklmm.jl_b200/blmm_b200/_lib.py, tests/test_gpu_*.py); the struct layouts below mirror
+# `_lib.Problem` / `_lib.Opts` field by field.  See INTEGRATION.md for how a maintainer wires it in.
+module BulkLMMB200
+
+using LinearAlgebra, Random, Statistics
+
+export bulkscan, bulkscan_null, bulkscan_null_grid, bulkscan_alt_grid, scan, calcKinship, transform_rotation,
+       get_thresholds
+
+const libblmm = get(ENV, "BLMM_B200_LIB", "libblmm_b200.so")
+
+# ---- mirrors of include/blmm_b200.h ------------------------------------------------------------------
+const BLMM_MEM_HOST = Cint(0)
+const METHOD_NULL_GRID, METHOD_ALT_GRID, METHOD_NULL_EXACT = Cint(0), Cint(1), Cint(2)
+const H2PANEL_REFERENCE, H2PANEL_ARGMAX = Cint(0), Cint(1)
+const DECOMP_EIGEN, DECOMP_SVD = Cint(0), Cint(1)
+
+struct BlmmProblem            # blmm_problem
+    n::Int64; p::Int64; m::Int64; c::Int64
+    Y::Ptr{Float64}; G::Ptr{Float64}; Covar::Ptr{Float64}; U::Ptr{Float64}; lambda::Ptr{Float64}
+end
+
+struct BlmmOpts               # blmm_opts
+    method::Int32; reml::Int32
+    prior_variance::Float64; prior_sample_size::Float64
+    h2_grid::Ptr{Float64}; ngrid::Int32
+    optim_interval::Int32; h2_panel_mode::Int32; mem_space::Int32
+    ld_out::Int64
+end
+
+mutable struct Context
+    handle::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        st = ccall((:blmm_create, libblmm), Cint, (Ref{Ptr{Cvoid}}, Cint), h, device)
+        st == 0 || error("blmm_create failed (status $st): no usable sm_100 (B200) device")
+        ctx = new(h[])
+        finalizer(c -> ccall((:blmm_destroy, libblmm), Cvoid, (Ptr{Cvoid},), c.handle), ctx)
+        return ctx
+    end
+end
+
+const _default_ctx = Ref{Union{Nothing, Context}}(nothing)
+default_context() = (_default_ctx[] === nothing && (_default_ctx[] = Context(0)); _default_ctx[])
+
+# The library reports the reference's own error strings; re-throw them as `error(msg)` so that code and
+# tests matching on `e.msg` keep working (e.g. "Dimension mismatch.", src/transform_helpers.jl:9-11).
+function check(ctx::Context, st::Cint)
+    st == 0 && return nothing
+    msg = unsafe_string(ccall((:blmm_last_error, libblmm), Cstring, (Ptr{Cvoid},), ctx.handle))
+    throw(error(msg))
+end
+
+# ---- setup -------------------------------------------------------------------------------------------
+function calcKinship(geno::Array{Float64, 2}; ctx::Context = default_context())
+    (n, p) = size(geno)
+    K = Array{Float64, 2}(undef, n, n)
+    GC.@preserve geno K check(ctx, ccall((:blmm_kinship, libblmm), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Cint), ctx.handle, n, p, geno, K, BLMM_MEM_HOST))
+    return K
+end
+
+function decompose(K::Array{Float64, 2}; decomp_scheme::String = "eigen", ctx::Context = default_context())
+    decomp_scheme in ("eigen", "svd") ||
+        throw(error("Please choose either `eigen` or `svd` for decomposition of the kinship matrix."))
+    n = size(K, 1)
+    U = Array{Float64, 2}(undef, n, n); lambda = Array{Float64, 1}(undef, n); nneg = Ref{Cint}(0)
+    GC.@preserve K U lambda check(ctx, ccall((:blmm_decompose, libblmm), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Ptr{Float64}, Ref{Cint}, Cint),
+        ctx.handle, n, K, decomp_scheme == "eigen" ? DECOMP_EIGEN : DECOMP_SVD, U, lambda, nneg, BLMM_MEM_HOST))
+    nneg[] > 0 && @warn "Negative eigenvalues exist. The kinship matrix supplied may not be SPD."
+    return U, lambda
+end
+
+function transform_rotation(y::Array{Float64, 2}, g::Array{Float64, 2}, K::Array{Float64, 2};
+                            addIntercept::Bool = true, decomp_scheme::String = "eigen",
+                            ctx::Context = default_context())
+    n = size(y, 1)
+    if (size(g, 1) != n) | (size(K, 1) != n)
+        throw(error("Dimension mismatch."))
+    end
+    X = addIntercept ? [ones(n, 1) g] : g
+    U, lambda = decompose(K; decomp_scheme = decomp_scheme, ctx = ctx)
+    Y0 = similar(y); X0 = similar(X)
+    prob = BlmmProblem(n, 0, size(y, 2), size(X, 2), pointer(y), C_NULL, pointer(X), pointer(U), pointer(lambda))
+    GC.@preserve y X U lambda Y0 X0 check(ctx, ccall((:blmm_rotate, libblmm), Cint,
+        (Ptr{Cvoid}, Ref{BlmmProblem}, Ptr{Float64}, Ptr{Float64}, Cint), ctx.handle, prob, Y0, X0, BLMM_MEM_HOST))
+    return Y0, X0, lambda
+end
+
+# Argument plumbing shared by the bulkscan methods: intercept column and the observation-weight
+# pre-scaling block of src/bulkscan.jl:231-250, 351-370, 457-476.
+function prep(Y, G, Covar, K, weights, addIntercept)
+    n = size(Y, 1)
+    if (size(G, 1) != n) | (size(K, 1) != n)
+        throw(error("Dimension mismatch."))
+    end
+    C = addIntercept ? [ones(n, 1) Covar] : Covar
+    if !ismissing(weights)
+        Y = weights .* Y; G = weights .* G; C = weights .* C
+        K = weights .* K .* weights'
+    end
+    return Array{Float64, 2}(Y), Array{Float64, 2}(G), Array{Float64, 2}(C), Array{Float64, 2}(K)
+end
+
+function run_bulkscan(method::Cint, Y, G, C, K, grid::Array{Float64, 1}; reml, prior_variance, prior_sample_size,
+                      optim_interval, decomp_scheme, h2_panel_mode = H2PANEL_REFERENCE, ctx = default_context())
+    (n, m) = size(Y); p = size(G, 2)
+    U, lambda = decompose(K; decomp_scheme = decomp_scheme, ctx = ctx)
+    L = Array{Float64, 2}(undef, p, m)
+    H = method == METHOD_ALT_GRID ? Array{Float64, 2}(undef, p, m) : Array{Float64, 1}(undef, m)
+    prob = BlmmProblem(n, p, m, size(C, 2), pointer(Y), pointer(G), pointer(C), pointer(U), pointer(lambda))
+    opts = BlmmOpts(method, reml, prior_variance, prior_sample_size, pointer(grid), length(grid), optim_interval,
+                    h2_panel_mode, BLMM_MEM_HOST, 0)
+    GC.@preserve Y G C U lambda grid L H check(ctx, ccall((:blmm_bulkscan, libblmm), Cint,
+        (Ptr{Cvoid}, Ref{BlmmProblem}, Ref{BlmmOpts}, Ptr{Float64}, Ptr{Float64}), ctx.handle, prob, opts, L, H))
+    return L, H
+end
+
+# ---- bulkscan family (src/bulkscan.jl) ------------------------------------------------------------------
+function bulkscan_null_grid(Y::Array{Float64, 2}, G::Array{Float64, 2}, Covar::Array{Float64, 2},
+                            K::Array{Float64, 2}, grid_list::Array{Float64, 1};
+                            weights::Union{Missing, Array{Float64, 1}} = missing, addIntercept::Bool = true,
+                            prior_variance::Float64 = 1.0, prior_sample_size::Float64 = 0.0, reml::Bool = false,
+                            decomp_scheme::String = "eigen")
+    Ys, Gs, Cs, Ks = prep(Y, G, Covar, K, weights, addIntercept)
+    L, h2 = run_bulkscan(METHOD_NULL_GRID, Ys, Gs, Cs, Ks, grid_list; reml = reml, prior_variance = prior_variance,
+                         prior_sample_size = prior_sample_size, optim_interval = 1, decomp_scheme = decomp_scheme)
+    return (L = L, h2_null_list = h2)
+end
+bulkscan_null_grid(Y, G, K, grid_list; kw...) =
+    bulkscan_null_grid(Y, G, ones(size(Y, 1), 1), K, grid_list; addIntercept = false, kw...)
+
+function bulkscan_alt_grid(Y::Array{Float64, 2}, G::Array{Float64, 2}, Covar::Array{Float64, 2},
+                           K::Array{Float64, 2}, hsq_list::Array{Float64, 1};
+                           weights::Union{Missing, Array{Float64, 1}} = missing, addIntercept::Bool = true,
+                           prior_variance::Float64 = 1.0, prior_sample_size::Float64 = 0.0, reml::Bool = false,
+                           decomp_scheme::String = "eigen")
+    Ys, Gs, Cs, Ks = prep(Y, G, Covar, K, weights, addIntercept)
+    L, h2_panel = run_bulkscan(METHOD_ALT_GRID, Ys, Gs, Cs, Ks, hsq_list; reml = reml, prior_variance = prior_variance,
+                               prior_sample_size = prior_sample_size, optim_interval = 1,
+                               decomp_scheme = decomp_scheme)
+    return (L = L, h2_panel = h2_panel)
+end
+bulkscan_alt_grid(Y, G, K, hsq_list; kw...) =
+    bulkscan_alt_grid(Y, G, ones(size(Y, 1), 1), K, hsq_list; addIntercept = false, kw...)
+
+function bulkscan_null(Y::Array{Float64, 2}, G::Array{Float64, 2}, Covar::Array{Float64, 2}, K::Array{Float64, 2};
+                       nb::Int64 = Threads.nthreads(), nt_blas::Int64 = 1,   # CPU threading knobs: accepted, unused
+                       weights::Union{Missing, Array{Float64, 1}} = missing, addIntercept::Bool = true,
+                       prior_variance::Float64 = 1.0, prior_sample_size::Float64 = 0.0, reml::Bool = false,
+                       optim_interval::Int64 = 1, decomp_scheme::String = "eigen")
+    Ys, Gs, Cs, Ks = prep(Y, G, Covar, K, weights, addIntercept)
+    L, h2 = run_bulkscan(METHOD_NULL_EXACT, Ys, Gs, Cs, Ks, Float64[0.0]; reml = reml, prior_variance = prior_variance,
+                         prior_sample_size = prior_sample_size, optim_interval = optim_interval,
+                         decomp_scheme = decomp_scheme)
+    return (L = L, h2_null_list = h2)
+end
+bulkscan_null(Y, G, K; kw...) = bulkscan_null(Y, G, ones(size(Y, 1), 1), K; addIntercept = false, kw...)
+
+function bulkscan(Y::Array{Float64, 2}, G::Array{Float64, 2}, Covar::Array{Float64, 2}, K::Array{Float64, 2};
+                  method::String = "null-grid", h2_grid::Array{Float64, 1} = collect(0.0:0.1:0.9),
+                  nb::Int64 = Threads.nthreads(), nt_blas::Int64 = 1,
+                  weights::Union{Missing, Array{Float64, 1}} = missing, addIntercept::Bool = true,
+                  prior_variance::Float64 = 1.0, prior_sample_size::Float64 = 0.0, reml::Bool = false,
+                  optim_interval::Int64 = 1, decomp_scheme::String = "eigen")
+    kw = (weights = weights, addIntercept = addIntercept, prior_variance = prior_variance,
+          prior_sample_size = prior_sample_size, reml = reml, decomp_scheme = decomp_scheme)
+    if method == "null-exact"
+        return bulkscan_null(Y, G, Covar, K; nb = nb, nt_blas = nt_blas, optim_interval = optim_interval, kw...)
+    elseif method == "null-grid"
+        return bulkscan_null_grid(Y, G, Covar, K, h2_grid; kw...)
+    elseif method == "alt-grid"
+        return bulkscan_alt_grid(Y, G, Covar, K, h2_grid; kw...)
+    end
+    throw(error("unknown method"))
+end
+bulkscan(Y::Array{Float64, 2}, G::Array{Float64, 2}, K::Array{Float64, 2}; kw...) =
+    bulkscan(Y, G, ones(size(Y, 1), 1), K; addIntercept = false, kw...)
+
+# ---- scan with permutations (src/scan.jl:485-557) ------------------------------------------------------
+# The shuffles are drawn HERE with the reference's own RNG and seed (src/transform_helpers.jl:94-102,
+# src/util.jl:162-179) and cross the ABI as 0-based indices, so permuted inputs match the reference
+# bit for bit whatever the Julia version's MersenneTwister stream is.
+function permutation_indices(n::Int64, nperms::Int64, rndseed::Int64)
+    rng = MersenneTwister(rndseed)
+    idx = Array{Int32, 2}(undef, n, nperms)
+    base = collect(1:n)
+    for s in 1:nperms
+        idx[:, s] = Int32.(shuffle(rng, base) .- 1)   # shuffle(rng, x) permutes positions identically for any x
+    end
+    return idx
+end
+
+function scan(y::Array{Float64, 2}, g::Array{Float64, 2}, covar::Array{Float64, 2}, K::Array{Float64, 2};
+              weights::Union{Missing, Array{Float64, 1}} = missing, prior_variance::Float64 = 0.0,
+              prior_sample_size::Float64 = 0.0, addIntercept::Bool = true, reml::Bool = false,
+              assumption::String = "null", method::String = "qr", optim_interval::Int64 = 1,
+              permutation_test::Bool = false, nperms::Int64 = 1024, rndseed::Int64 = 0,
+              decomp_scheme::String = "eigen", ctx::Context = default_context())
+    assumption == "null" || throw(error("Assumption keyword is not supported. Please enter null or alt."))
+    permutation_test || throw(error("scan without permutation_test: use bulkscan(...; method = \"null-exact\")"))
+    size(y, 2) == 1 || throw(error("Can only handle one trait."))
+    ys, gs, cs, Ks = prep(y, g, covar, K, weights, addIntercept)
+    (n, p) = size(gs)
+    U, lambda = decompose(Ks; decomp_scheme = decomp_scheme, ctx = ctx)
+    perm = permutation_indices(n, nperms, rndseed)
+    lod = Array{Float64, 1}(undef, p); L_perms = Array{Float64, 2}(undef, p, nperms)
+    maxlod = Array{Float64, 1}(undef, nperms); s2 = Ref{Float64}(0.0); h2 = Ref{Float64}(0.0)
+    prob = BlmmProblem(n, p, 1, size(cs, 2), pointer(ys), pointer(gs), pointer(cs), pointer(U), pointer(lambda))
+    opts = BlmmOpts(METHOD_NULL_EXACT, reml, prior_variance, prior_sample_size, C_NULL, 0, optim_interval,
+                    H2PANEL_REFERENCE, BLMM_MEM_HOST, 0)
+    GC.@preserve ys gs cs U lambda perm lod L_perms maxlod check(ctx, ccall((:blmm_scan_perms, libblmm), Cint,
+        (Ptr{Cvoid}, Ref{BlmmProblem}, Ref{BlmmOpts}, Ptr{Int32}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ref{Float64}, Ref{Float64}), ctx.handle, prob, opts, perm, nperms, lod, L_perms, maxlod, s2, h2))
+    return (sigma2_e = s2[], h2_null = h2[], lod = lod, L_perms = L_perms)
+end
+function scan(y::Array{Float64, 2}, g::Array{Float64, 2}, K::Array{Float64, 2}; addIntercept::Bool = true, kw...)
+    addIntercept || throw(error("Intercept has to be added when no other covariate is given."))
+    return scan(y, g, ones(size(y, 1), 1), K; addIntercept = false, kw...)
+end
+scan(y::Array{Float64, 1}, g::Array{Float64, 2}, K::Array{Float64, 2}; kw...) = scan(reshape(y, :, 1), g, K; kw...)
+
+# src/analysis_helpers/single_trait_analysis.jl:13-23
+function get_thresholds(L::Array{Float64, 2}, signif_level::Array{Float64, 1})
+    thrs = map(x -> quantile(vec(maximum(L, dims = 1)), 1 - x), signif_level)
+    return (probs = 1 .- signif_level, thrs = thrs)
+end
+
+end # module
