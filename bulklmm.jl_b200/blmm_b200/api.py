@@ -211,6 +211,20 @@ class Engine:
         self._check(self.lib.blmm_fit_h2(self.h, C.byref(pr), C.byref(o), _ptr(h2), _ptr(s2), _ptr(ell)))
         return h2, s2, ell
 
+    def scan_null_host(self, Y, G, Covar, U, lam, reml=False, prior_variance=0.0, prior_sample_size=0.0,
+                       optim_interval=1):
+        """blmm_scan_null: per-trait fitlmm + single-trait null scan for every column of Y."""
+        Y, G, Covar, U = _f(Y), _f(G), _f(Covar), _f(U)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        p, m = G.shape[1], Y.shape[1]
+        pr = self._host_problem(Y, G, Covar, U, lam)
+        o, _ = self.make_opts(method=L.METHOD_NULL_EXACT, reml=reml, prior_variance=prior_variance,
+                              prior_sample_size=prior_sample_size, optim_interval=optim_interval)
+        lod = np.empty((p, m), order="F")
+        s2, h2 = np.empty(m), np.empty(m)
+        self._check(self.lib.blmm_scan_null(self.h, C.byref(pr), C.byref(o), _ptr(lod), _ptr(s2), _ptr(h2)))
+        return lod, s2, h2
+
     def scan_perms_host(self, y, G, Covar, U, lam, perm_idx, reml=False, prior_variance=0.0,
                         prior_sample_size=0.0, optim_interval=1, want_L=True, want_max=True):
         y, G, Covar, U = _f(y), _f(G), _f(Covar), _f(U)
@@ -356,12 +370,19 @@ def scan(y, g, K, covar=None, weights=None, prior_variance: float = 0.0, prior_s
         raise BlmmError(L.E_INVALID, "Intercept has to be added when no other covariate is given.")
     if assumption != "null":
         raise BlmmError(L.E_INVALID, "Assumption keyword is not supported. Please enter null or alt.")
-    if not permutation_test:
-        raise BlmmError(L.E_INVALID, "scan without permutation_test is served by bulkscan(method=\"null-exact\")")
     if y.shape[1] != 1:
         raise BlmmError(L.E_ONE_TRAIT, "Can only handle one trait.")
     y, g, C0, K = _prep(y, g, covar, K, weights, addIntercept)
     n = y.shape[0]
+    if not permutation_test:
+        # scan_null, src/scan.jl:310-360
+        if decomposition is None:
+            U, lam, _ = eng.decompose(K, decomp_scheme)
+        else:
+            U, lam = decomposition
+        lod, s2, h2 = eng.scan_null_host(y, g, C0, U, lam, reml=reml, prior_variance=prior_variance,
+                                         prior_sample_size=prior_sample_size, optim_interval=optim_interval)
+        return SimpleNamespace(sigma2_e=float(s2[0]), h2_null=float(h2[0]), lod=lod[:, 0].copy())
     if perm_idx is None:
         from .synth import make_perm_indices
         perm_idx = make_perm_indices(n, nperms, rndseed)

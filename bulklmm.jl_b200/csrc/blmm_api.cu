@@ -21,7 +21,8 @@ using namespace blmm;
 enum Slot {
   S_Y_IN, S_G_IN, S_C_IN, S_U_IN, S_LAM, S_GRID, S_Y0, S_C0, S_G0, S_YR, S_W, S_SW, S_Q, S_SLW, S_LDS,
   S_ELL, S_RSS, S_BEST, S_ELLMAX, S_MOP, S_TOP, S_E, S_ET, S_BINS, S_TILEK0, S_COLMAP, S_L, S_H2P, S_H2V,
-  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_LOGTAB, S_COUNT
+  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_LOGTAB, S_XOP, S_DYINV,
+  S_COUNT
 };
 
 struct blmm_ctx {
@@ -179,19 +180,24 @@ void run_scan(blmm_ctx* ctx, ScanParams P) {
   }
   P.logtab = reinterpret_cast<const double*>(ctx->buf[S_LOGTAB]);
   if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-  ctx->launches += launch_scan(P, ctx->sm_count, ctx->stream);
+  if (P.nq <= scan_max_nq(P.nk)) {
+    ctx->launches += launch_scan(P, ctx->sm_count, ctx->stream);
+  } else {
+    // n too large for the shared-memory-resident trait tile: same arithmetic, K streamed
+    static_assert(SCAN_TT == 128 && SCAN_MT == 64, "packing shared with the streamed GRID kernel");
+    StreamParams Q{};
+    Q.Mop = P.Mop; Q.Xop = P.Top; Q.e = P.e; Q.et = P.et; Q.tile_k0 = P.tile_k0; Q.n_tiles_dev = P.n_tiles_dev;
+    Q.col_map = P.col_map; Q.grid = P.grid; Q.logtab = P.logtab; Q.ngrid = P.ngrid; Q.L = P.L; Q.L0 = P.L0;
+    Q.H2 = P.H2; Q.colmax = P.colmax; Q.ldL = P.ldL; Q.nq = P.nq; Q.p = P.p; Q.p_pad = P.p_pad; Q.m = P.m;
+    Q.xcol_pad = P.tcol_pad; Q.tcol_pad = P.tcol_pad; Q.n_tt = P.n_tiles_t; Q.nk = P.nk;
+    Q.argmax_mode = P.argmax_mode; Q.half_n = P.half_n;
+    ctx->launches += launch_scan_stream_grid(Q, ctx->sm_count, ctx->stream);
+  }
   if (ctx->profiling) {
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->scan_timed = true;
   }
   CUDA_TRY(cudaGetLastError());
-}
-
-void require_resident(int nq) {
-  if (nq > scan_max_nq(1))
-    throw Fail{BLMM_E_INVALID, "n = " + std::to_string(nq * KC) +
-                                   " (padded) exceeds the shared-memory-resident scan kernel (n <= " +
-                                   std::to_string(scan_max_nq(1) * KC) + ")"};
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -208,7 +214,6 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   reset_flags(ctx);
   const double* d_grid = upload_grid(ctx, o);
   Rotated R = rotate_inputs(ctx, pr, ms, true);
-  require_resident(R.nq);
   WeightConsts wc = weight_ws(ctx, nk, R.n_pad, R.c);
   ctx->launches += launch_weight_consts(d_grid, nk, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags, ctx->stream);
 
@@ -229,7 +234,7 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
 
   const int64_t p_pad = round_up(p, SCAN_MT);
   double* Mop = ws<double>(ctx, S_MOP, (size_t)nk * R.n_pad * p_pad);
-  ctx->launches += launch_marker_operand(R.G0, p, p_pad, R.n, R.n_pad, R.c, nk, wc, Mop, ctx->d_flags, ctx->stream);
+  ctx->launches += launch_marker_operand(R.G0, p, p_pad, R.n, R.n_pad, R.c, nk, wc, true, Mop, ctx->d_flags, ctx->stream);
 
   ScanParams P{};
   P.Mop = Mop;
@@ -360,6 +365,77 @@ int fit_h2(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, double* h2
   return BLMM_OK;
 }
 
+// bulkscan_null (src/bulkscan.jl:212-314): per-trait Brent h2, then univar_liteqtl with the trait's own
+// weights as c+2 operand columns (blmm_scan_stream.cu, EXACT mode).  sigma2_out is optional (scan_null).
+int bulkscan_exact(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, double* L_out, double* h2_out,
+                   double* sigma2_out) {
+  check_problem(pr, true);
+  if (!L_out) throw Fail{BLMM_E_INVALID, "L_out is NULL"};
+  if (o->optim_interval < 1) throw Fail{BLMM_E_INVALID, "optim_interval must be >= 1"};
+  const int ms = o->mem_space;
+  const bool dev = ms == BLMM_MEM_DEVICE;
+  const int64_t p = pr->p, m = pr->m;
+  const int64_t ld = o->ld_out ? o->ld_out : p;
+  if (ld < p) throw Fail{BLMM_E_INVALID, "ld_out < p"};
+  if (m == 0) return BLMM_OK;
+  reset_flags(ctx);
+  Rotated R = rotate_inputs(ctx, pr, ms, true);
+  double* Yr = residualised_traits(ctx, R, o);  // also leaves the w = 1 constants in weight slot 0
+  double* h2 = (dev && h2_out) ? h2_out : ws<double>(ctx, S_H2V, m);
+  double* s2 = (dev && sigma2_out) ? sigma2_out : ws<double>(ctx, S_SIG2, m);
+  ctx->launches += launch_fit_h2(Yr, m, R.n, R.n_pad, R.c, R.C0, R.lambda, lik_of(o), o->optim_interval, h2, s2,
+                                 nullptr, ctx->d_flags, ctx->stream);
+  // markers residualised (unweighted) on the covariates and normalised: r^2 is invariant to both
+  const int mt = stream_exact_marker_tile(R.c);
+  const int64_t p_pad = round_up(p, mt);
+  WeightConsts wc0 = weight_ws(ctx, 0, R.n_pad, R.c);
+  double* Mop = ws<double>(ctx, S_MOP, (size_t)R.n_pad * p_pad);
+  ctx->launches += launch_marker_operand(R.G0, p, p_pad, R.n, R.n_pad, R.c, 1, wc0, false, Mop, ctx->d_flags, ctx->stream);
+  const int cg = R.c + 2;
+  const int64_t n_tt = (m + 63) / 64;
+  const int64_t slots = n_tt * 64;
+  const int64_t xcol_pad = slots * cg;
+  double* Xop = ws<double>(ctx, S_XOP, (size_t)R.n_pad * xcol_pad);
+  double* dyinv = ws<double>(ctx, S_DYINV, slots);
+  ctx->launches += launch_exact_columns(Yr, h2, R.lambda, R.C0, m, slots, R.n, R.n_pad, R.c, Xop, xcol_pad, dyinv,
+                                        ctx->d_flags, ctx->stream);
+  if (!ctx->buf[S_LOGTAB]) {
+    double* tab = ws<double>(ctx, S_LOGTAB, scan_logtab_doubles());
+    ctx->launches += launch_logtab(tab, ctx->stream);
+  }
+  StreamParams P{};
+  P.Mop = Mop;
+  P.Xop = Xop;
+  P.dyinv = dyinv;
+  P.logtab = reinterpret_cast<const double*>(ctx->buf[S_LOGTAB]);
+  double* dL = dev ? L_out : ws<double>(ctx, S_L, (size_t)p * m);
+  P.L = dL;
+  P.ldL = dev ? ld : p;
+  P.nq = R.nq;
+  P.p = (int)p;
+  P.p_pad = (int)p_pad;
+  P.m = m;
+  P.xcol_pad = xcol_pad;
+  P.n_tt = (int)n_tt;
+  P.nk = 1;
+  P.half_n = (double)R.n / 2.0;
+  if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  ctx->launches += launch_scan_exact(P, R.c, ctx->sm_count, ctx->stream);
+  if (ctx->profiling) {
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->scan_timed = true;
+  }
+  CUDA_TRY(cudaGetLastError());
+  if (!dev) {
+    CUDA_TRY(cudaMemcpy2DAsync(L_out, ld * sizeof(double), dL, p * sizeof(double), p * sizeof(double), m,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    copy_out(ctx, h2_out, h2, m, ms);
+    copy_out(ctx, sigma2_out, s2, m, ms);
+    finish_and_check(ctx);
+  }
+  return BLMM_OK;
+}
+
 int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const int32_t* perm_idx, int64_t nperms,
                double* lod_out, double* Lperms_out, double* maxlod_out, double* sigma2_out, double* h2_out) {
   if (pr && pr->m != 1) throw Fail{BLMM_E_ONE_TRAIT, "Can only handle one trait."};
@@ -374,7 +450,6 @@ int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const 
   if (ld < p) throw Fail{BLMM_E_INVALID, "ld_out < p"};
   reset_flags(ctx);
   Rotated R = rotate_inputs(ctx, pr, ms, true);
-  require_resident(R.nq);
   double* Yr = residualised_traits(ctx, R, o);
   double* h2 = (dev && h2_out) ? h2_out : ws<double>(ctx, S_H2V, 1);
   double* s2 = (dev && sigma2_out) ? sigma2_out : ws<double>(ctx, S_SIG2, 1);
@@ -388,7 +463,7 @@ int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const 
   ctx->launches += launch_null_residual(Yr, R.n, R.n_pad, R.c, wc, z, zrss, ctx->stream);
   const int64_t p_pad = round_up(p, SCAN_MT);
   double* Mop = ws<double>(ctx, S_MOP, (size_t)R.n_pad * p_pad);
-  ctx->launches += launch_marker_operand(R.G0, p, p_pad, R.n, R.n_pad, R.c, 1, wc, Mop, ctx->d_flags, ctx->stream);
+  ctx->launches += launch_marker_operand(R.G0, p, p_pad, R.n, R.n_pad, R.c, 1, wc, false, Mop, ctx->d_flags, ctx->stream);
 
   const int64_t ncol = nperms + 1;
   const int64_t tcol_pad = round_up(ncol, SCAN_TT);
@@ -677,7 +752,7 @@ int blmm_bulkscan(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts
       case BLMM_METHOD_ALT_GRID:
         return bulkscan_grid(ctx, prob, opts, L_out, h2_out);
       case BLMM_METHOD_NULL_EXACT:
-        throw Fail{BLMM_E_INVALID, "method null-exact is not implemented yet"};
+        return bulkscan_exact(ctx, prob, opts, L_out, h2_out, nullptr);
       default:
         throw Fail{BLMM_E_INVALID, "unknown method"};
     }
@@ -710,8 +785,10 @@ int blmm_scan_perms(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* op
 
 int blmm_scan_null(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* lod_out,
                    double* sigma2_out, double* h2_out) {
-  (void)prob; (void)opts; (void)lod_out; (void)sigma2_out; (void)h2_out;
-  return guarded(ctx, [&]() -> int { throw Fail{BLMM_E_INVALID, "blmm_scan_null is not implemented yet"}; });
+  return guarded(ctx, [&] {
+    if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
+    return bulkscan_exact(ctx, prob, opts, lod_out, h2_out, sigma2_out);
+  });
 }
 
 }  // extern "C"

@@ -55,11 +55,14 @@ int launch_trait_stats(const double* Y0, int64_t m, int n, int n_pad, int c, int
                        int* best, double* ellmax, double* h2_out, int* bin_count, int* flags,
                        cudaStream_t stream);
 
-// One warp per marker: Mop[k][q][i][kk] = sw_k .* (P_k (sw_k .* g_i)) / ||P_k (sw_k .* g_i)||
-// (weighted_liteqtl + computeR_LMM marker side, src/bulkscan_helpers.jl:175-201, 47-64, with the
-// trait-side sqrt(w) and projector folded in so the trait operand is weight independent).
+// One warp per marker: x = P_k (sw_k .* g_i) / ||P_k (sw_k .* g_i)||  (the normalised X00 column of
+// weighted_liteqtl + computeR_LMM, src/bulkscan_helpers.jl:175-201, 47-64).
+//   fold_sw = true : Mop[k][q][i][kk] = sw_k .* x — the trait-side sqrt(w) and projector folded in, so
+//                    the trait operand (unweighted residual) is weight independent (grid scans);
+//   fold_sw = false: Mop = x, for trait operands that are already weighted and projected
+//                    (permutations of the re-weighted null residual, src/scan.jl:531-541; w = 1 slot).
 int launch_marker_operand(const double* G0, int64_t p, int64_t p_pad, int n, int n_pad, int c, int nk,
-                          WeightConsts wc, double* Mop, int* flags, cudaStream_t stream);
+                          WeightConsts wc, bool fold_sw, double* Mop, int* flags, cudaStream_t stream);
 
 // alt-grid trait scalars: e[k][j] = exp(-2 (ell[k,j] - ellmax_j) / n), et = e / rss; pads e=1, et=0.
 int launch_alt_scalars(const double* ell, const double* rss, const double* ellmax, int64_t m,
@@ -140,5 +143,45 @@ int scan_max_nq(int nk);
 int scan_logtab_doubles();
 int launch_logtab(double* tab, cudaStream_t stream);
 int launch_scan(const ScanParams& P, int sm_count, cudaStream_t stream);
+
+// ---- the K-streamed scans (blmm_scan_stream.cu) -------------------------------------------------
+// Any n.  EXACT mode: per-trait weights (bulkscan_null); GRID mode: ScanParams' arithmetic.
+struct StreamParams {
+  const double* Mop;       // marker operand [nk_total][nq][p_pad][KC]  (EXACT: one slab, w = 1)
+  const double* Xop;       // trait operand  [nq][xcol_pad][KC]; EXACT: (c+2) column kinds per trait
+  const double* dyinv;     // EXACT: [n_tt*64] 1 / (y_j' z_j)
+  const double* e;         // GRID: [nk][tcol_pad] or nullptr (=> 1)
+  const double* et;        // GRID: [nk][tcol_pad]
+  const int* tile_k0;      // GRID: per trait tile first k, or nullptr
+  const int* n_tiles_dev;  // device scalar: trait tiles in use, or nullptr => n_tt
+  const int* col_map;      // packed column -> output column (-1 = padding); nullptr => identity
+  const double* grid;      // h2 grid (device), GRID mode h2 panel
+  const double* logtab;
+  int ngrid;
+  double* L;
+  double* L0;
+  double* H2;
+  double* colmax;
+  int64_t ldL;
+  int nq;
+  int p;
+  int p_pad;               // multiple of the marker tile
+  int64_t m;               // output columns
+  int64_t xcol_pad;        // operand columns of Xop
+  int64_t tcol_pad;        // GRID: padded packed-trait count (= xcol_pad)
+  int n_tt;                // trait tiles (EXACT: 64 traits each; GRID: stream_grid_trait_tile())
+  int nk;                  // GRID: k-list length
+  int argmax_mode;
+  double half_n;
+};
+int stream_exact_marker_tile(int c);  // marker tile of the EXACT kernel for c covariates
+int stream_grid_marker_tile();
+int stream_grid_trait_tile();
+// z_j, q_j1..q_jc, w_j columns and 1/dy_j of every trait at its own h2 (slots = n_tt*64 >= m)
+int launch_exact_columns(const double* Yr, const double* h2, const double* lambda, const double* C0, int64_t m,
+                         int64_t slots, int n, int n_pad, int c, double* Xop, int64_t xcol_pad, double* dyinv,
+                         int* flags, cudaStream_t stream);
+int launch_scan_exact(const StreamParams& P, int c, int sm_count, cudaStream_t stream);
+int launch_scan_stream_grid(const StreamParams& P, int sm_count, cudaStream_t stream);
 
 }  // namespace blmm

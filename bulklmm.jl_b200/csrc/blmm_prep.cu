@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
 
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
     marker_operand_kernel(const double* __restrict__ G0, int64_t p, int64_t p_pad, int n, int n_pad, int c, int nk,
-                          WeightConsts wc, double* __restrict__ Mop, int* flags) {
+                          WeightConsts wc, int fold_sw, double* __restrict__ Mop, int* flags) {
   extern __shared__ double smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wid;
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
     const double inv = 1.0 / nrm;
     for (int l = lane; l < n_pad; l += 32) {
       const double z = proj_elem(gb, sw, Q, n_pad, c, l, coef);
-      Mop[(((int64_t)k * nq + l / KC) * p_pad + i) * KC + (l % KC)] = sw[l] * z * inv;
+      Mop[(((int64_t)k * nq + l / KC) * p_pad + i) * KC + (l % KC)] = (fold_sw ? sw[l] * z : z) * inv;
     }
   }
 }
@@ -514,13 +514,13 @@ int launch_trait_stats(const double* Y0, int64_t m, int n, int n_pad, int c, int
 }
 
 int launch_marker_operand(const double* G0, int64_t p, int64_t p_pad, int n, int n_pad, int c, int nk,
-                          WeightConsts wc, double* Mop, int* flags, cudaStream_t stream) {
+                          WeightConsts wc, bool fold_sw, double* Mop, int* flags, cudaStream_t stream) {
   const size_t smem = (size_t)WARPS_PER_BLOCK * n_pad * sizeof(double);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(marker_operand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const unsigned blocks = (unsigned)((p_pad + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-  marker_operand_kernel<<<blocks, 32 * WARPS_PER_BLOCK, smem, stream>>>(G0, p, p_pad, n, n_pad, c, nk, wc, Mop,
-                                                                         flags);
+  marker_operand_kernel<<<blocks, 32 * WARPS_PER_BLOCK, smem, stream>>>(G0, p, p_pad, n, n_pad, c, nk, wc,
+                                                                         fold_sw ? 1 : 0, Mop, flags);
   return 1;
 }
 

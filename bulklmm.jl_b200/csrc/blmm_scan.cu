@@ -22,7 +22,6 @@ namespace {
 constexpr int TT = SCAN_TT;  // traits per CTA tile
 constexpr int MT = SCAN_MT;  // markers per CTA tile
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int LOGTAB_N = 128;
 #ifndef BLMM_SCAN_BT
 #define BLMM_SCAN_BT 2
 #endif
@@ -48,45 +47,6 @@ __host__ __device__ inline SmemPlan plan_smem(int nq) {
     s.bytes = (s.top_doubles + 2 * s.stage_doubles) * 8 + FIXED_SMEM;
   }
   return s;
-}
-
-// ---------------------------------------------------------------------------------------------
-// log10 for the final epilogue.  The FP64 pipe is shared by DMMA and scalar double arithmetic on
-// B200 (profiles/fp64_peak_r01.json: mixed loop), so the logarithm is kept to ~12 FP64
-// operations: v = 2^e * m, m in [0.75, 1.5); a 128-entry table gives rcp ~ 1/c and -log10(rcp)
-// for the interval of m; r = m*rcp - 1 (|r| <= 2^-7); log1p(r) by an 8-term series.  The two
-// intervals touching 1 use rcp = 1 exactly, so results keep full relative accuracy as v -> 1
-// (LOD -> 0).  Absolute error ~1e-16, far inside the 1e-8 parity tolerance.
-// `special` is raised for operands outside the positive normal range (fixed up by the caller).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double fast_log10(double v, const double2* __restrict__ tab, bool& special) {
-  const int hi = __double2hiint(v), lo = __double2loint(v);
-  const int ix = hi - 0x3fe80000;
-  const int e = ix >> 20;
-  const double m = __hiloint2double(hi - (e << 20), lo);
-  const double2 t = tab[(ix >> 13) & (LOGTAB_N - 1)];
-  const double r = fma(m, t.x, -1.0);
-  double q = fma(r, -1.0 / 8.0, 1.0 / 7.0);
-  q = fma(q, r, -1.0 / 6.0);
-  q = fma(q, r, 1.0 / 5.0);
-  q = fma(q, r, -1.0 / 4.0);
-  q = fma(q, r, 1.0 / 3.0);
-  q = fma(q, r, -1.0 / 2.0);
-  q = fma(q, r, 1.0);
-  const double lp = q * r;
-  special |= (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
-  return fma(lp, 0.43429448190325182765, fma((double)e, 0.30102999566398119521, t.y));
-}
-
-// IEEE results for the operands fast_log10 flags: v = 0 (r^2 = 1) -> -inf as log10 (a subnormal
-// v, unreachable as 1 - r^2, is treated as 0); v < 0 -> NaN (Julia's log10 throws there);
-// inf / NaN pass through.
-__device__ __forceinline__ double fix_log10(double v, double res) {
-  const int hi = __double2hiint(v);
-  res = ((unsigned)hi < 0x00100000u) ? -INFINITY : res;
-  res = (hi < 0) ? __longlong_as_double(0x7ff8000000000000LL) : res;
-  res = (hi >= 0x7ff00000) ? v : res;
-  return res;
 }
 
 // first k-step of a tile: C = 0 (no separate zeroing of the accumulators)

@@ -212,11 +212,20 @@ function scan(y::Array{Float64, 2}, g::Array{Float64, 2}, covar::Array{Float64, 
               permutation_test::Bool = false, nperms::Int64 = 1024, rndseed::Int64 = 0,
               decomp_scheme::String = "eigen", ctx::Context = default_context())
     assumption == "null" || throw(error("Assumption keyword is not supported. Please enter null or alt."))
-    permutation_test || throw(error("scan without permutation_test: use bulkscan(...; method = \"null-exact\")"))
     size(y, 2) == 1 || throw(error("Can only handle one trait."))
     ys, gs, cs, Ks = prep(y, g, covar, K, weights, addIntercept)
     (n, p) = size(gs)
     U, lambda = decompose(Ks; decomp_scheme = decomp_scheme, ctx = ctx)
+    if !permutation_test        # scan_null, src/scan.jl:310-360
+        lod = Array{Float64, 2}(undef, p, 1); s2 = Ref{Float64}(0.0); h2 = Ref{Float64}(0.0)
+        prob = BlmmProblem(n, p, 1, size(cs, 2), pointer(ys), pointer(gs), pointer(cs), pointer(U), pointer(lambda))
+        opts = BlmmOpts(METHOD_NULL_EXACT, reml, prior_variance, prior_sample_size, C_NULL, 0, optim_interval,
+                        H2PANEL_REFERENCE, BLMM_MEM_HOST, 0)
+        GC.@preserve ys gs cs U lambda lod check(ctx, ccall((:blmm_scan_null, libblmm), Cint,
+            (Ptr{Cvoid}, Ref{BlmmProblem}, Ref{BlmmOpts}, Ptr{Float64}, Ref{Float64}, Ref{Float64}),
+            ctx.handle, prob, opts, lod, s2, h2))
+        return (sigma2_e = s2[], h2_null = h2[], lod = vec(lod))
+    end
     perm = permutation_indices(n, nperms, rndseed)
     lod = Array{Float64, 1}(undef, p); L_perms = Array{Float64, 2}(undef, p, nperms)
     maxlod = Array{Float64, 1}(undef, nperms); s2 = Ref{Float64}(0.0); h2 = Ref{Float64}(0.0)
