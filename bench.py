@@ -186,12 +186,13 @@ def workload_config(workload, gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="alt-grid", choices=["alt-grid", "null-grid"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other configs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -337,6 +338,48 @@ def main():
         # sanity: host and device paths agree
         assert torch.equal(pL, dL.cpu()), "host-buffer result differs from device-resident result"
 
+    # ---- the other BASELINE.json configs on one GPU, device-resident, a few steps each (context for the
+    # headline number, not part of it)
+    other = None
+    if world == 1 and not args.no_other:
+        other = {}
+
+        def timed(fn, reps=3):
+            fn(); eng.sync()
+            ms, ks = [], []
+            for _ in range(reps):
+                with torch.cuda.stream(stream):
+                    flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream); fn(); b.record(stream); eng.sync()
+                ms.append(a.elapsed_time(b)); ks.append(eng.last_scan_ms())
+            return float(np.mean(ms)), float(np.mean(ks))
+
+        dh = torch.empty(ml, dtype=torch.float64, device=dev)
+        for name, meth, kw, fl in (("null-grid", L.METHOD_NULL_GRID, dict(h2_grid=GRID), 2.0 * n * p * ml),
+                                   ("null-exact (REML Brent per trait)", L.METHOD_NULL_EXACT, dict(reml=True, prior_variance=0.0),
+                                    2.0 * n * p * ml * 3)):
+            if alt is False and name == "null-grid":
+                continue
+            o2, keep3 = eng.make_opts(method=meth, mem_space=L.MEM_DEVICE, **kw)
+            t_ms, k_ms = timed(lambda: eng.bulkscan_raw(pr, o2, dL.data_ptr(), dh.data_ptr()))
+            other[name] = {"ms_per_step": t_ms, "tests_per_s": p * ml / (t_ms * 1e-3), "scan_kernel_ms": k_ms,
+                           "scan_kernel_tflops": fl / (k_ms * 1e-3) / 1e12}
+        nperms = 10000
+        perm = torch.from_numpy(np.ascontiguousarray(synth.make_perm_indices(n, nperms, 0).T)).to(dev)
+        dy1 = dY[1111:1112].contiguous()
+        pr1 = eng.make_problem(n, p, 1, 1, dy1.data_ptr(), dG.data_ptr(), dC.data_ptr(), dU.data_ptr(), dl.data_ptr())
+        o3, _k = eng.make_opts(method=L.METHOD_NULL_EXACT, prior_variance=0.0, mem_space=L.MEM_DEVICE)
+        lod1 = torch.empty(p, dtype=torch.float64, device=dev)
+        mx = torch.empty(nperms, dtype=torch.float64, device=dev)
+        sc = torch.empty(2, dtype=torch.float64, device=dev)
+        for name, lp in (("scan 1 trait x 10000 permutations, per-permutation max only", None),
+                         ("scan 1 trait x 10000 permutations, L_perms materialised", dL.data_ptr())):
+            t_ms, k_ms = timed(lambda: eng.scan_perms_raw(pr1, o3, perm.data_ptr(), nperms, lod1.data_ptr(), lp,
+                                                          mx.data_ptr(), sc.data_ptr(), sc.data_ptr() + 8))
+            other[name] = {"ms_per_step": t_ms, "tests_per_s": p * (nperms + 1) / (t_ms * 1e-3), "scan_kernel_ms": k_ms,
+                           "scan_kernel_tflops": 2.0 * n * p * (nperms + 1) / (k_ms * 1e-3) / 1e12}
+
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:
         cpu = cpu_baseline(args.workload, 2048 if alt else 8192)
@@ -348,6 +391,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": workload_config(args.workload, world), "roofline": roofline,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "other_workloads": other,
                 "setup_ms": {"eigendecomposition_first_call": setup_ms, "eigendecomposition_warm": setup_ms_warm},
                 "reference_published": README_REF}
         print(json.dumps(line), flush=True)

@@ -29,6 +29,8 @@ struct blmm_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap the scan (host-buffer calls)
+  cudaEvent_t chunk_ev[16] = {};
   cusolverDnHandle_t solver = nullptr;
   void* buf[S_COUNT] = {};
   size_t cap[S_COUNT] = {};
@@ -284,6 +286,36 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     P.tcol_pad = tcol_pad;
     P.n_tiles_t = (int)(tcol_pad / SCAN_TT);
     P.nk = 1;
+  }
+  if (ms == BLMM_MEM_HOST && alt && P.n_tiles_t >= 16) {
+    // Host-buffer alt-grid: the p x m panels (2 x 2 GB at BXD size) leave over PCIe, which takes ~5x
+    // the scan itself.  Scan the trait tiles in chunks and copy each chunk's columns back on a
+    // second stream while the next chunk is scanned.
+    const int nchunk = 8;
+    const int n_tiles = P.n_tiles_t;
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const int t0 = (int)((int64_t)n_tiles * ch / nchunk), t1 = (int)((int64_t)n_tiles * (ch + 1) / nchunk);
+      const int64_t c0 = (int64_t)t0 * SCAN_TT, c1 = std::min<int64_t>((int64_t)t1 * SCAN_TT, m);
+      ScanParams Pc = P;
+      Pc.Top = P.Top + c0 * KC;
+      Pc.e = P.e + c0;
+      Pc.et = P.et + c0;
+      Pc.L = dL + c0 * p;
+      Pc.H2 = dH ? dH + c0 * p : nullptr;
+      Pc.m = m - c0;
+      Pc.n_tiles_t = t1 - t0;
+      run_scan(ctx, Pc);
+      CUDA_TRY(cudaEventRecord(ctx->chunk_ev[ch], ctx->stream));
+      CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[ch], 0));
+      CUDA_TRY(cudaMemcpy2DAsync(L_out + c0 * ld, ld * sizeof(double), dL + c0 * p, p * sizeof(double),
+                                 p * sizeof(double), c1 - c0, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      if (dH)
+        CUDA_TRY(cudaMemcpy2DAsync(h2_out + c0 * ld, ld * sizeof(double), dH + c0 * p, p * sizeof(double),
+                                   p * sizeof(double), c1 - c0, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    finish_and_check(ctx);
+    CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    return BLMM_OK;
   }
   run_scan(ctx, P);
 
@@ -640,6 +672,7 @@ int guarded(blmm_ctx* ctx, F&& f) {
   } catch (const Fail& fl) {
     ctx->err = fl.msg;
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     cudaGetLastError();
     return fl.code;
   } catch (const std::exception& ex) {
@@ -677,9 +710,11 @@ int blmm_create(blmm_ctx** out, int device) {
   ctx->sm_count = prop.multiProcessorCount;
   bool ok = cudaSetDevice(device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc(&ctx->d_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaMallocHost(&ctx->h_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
+  for (int i = 0; ok && i < 16; ++i) ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     blmm_destroy(ctx);
     return BLMM_E_CUDA;
@@ -699,6 +734,9 @@ void blmm_destroy(blmm_ctx* ctx) {
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < 16; ++i)
+    if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -70,6 +70,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
+// The same copy with an L2 cache-policy hint (createpolicy), e.g. evict_last for operands that are
+// re-read many times while large outputs stream through L2.
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 // FP64 tensor-core atom: D(8x8) += A(8x4, row) * B(4x8, col).  Lane l = 4*g + t holds
 // a = A[g][t], b = B[t][g], c0/c1 = C[g][2t], C[g][2t+1].  SASS: DMMA.8x8x4.
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

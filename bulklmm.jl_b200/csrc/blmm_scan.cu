@@ -77,6 +77,9 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  // The marker operand (all k) is re-read by every trait tile: ask L2 to keep it while the LOD /
+  // h2 panels stream through (they are written with evict-first stores).
+  const uint64_t keep_policy = l2_evict_last_policy();
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
     const double* src = P.Mop + (((size_t)(k0 + kk) * NQ) * P.p_pad + (size_t)mt * MT) * KC;
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
-      bulk_g2s(st + (size_t)q * MT * KC, src + (size_t)q * P.p_pad * KC, marker_chunk_bytes, &full[s]);
+      bulk_g2s_hint(st + (size_t)q * MT * KC, src + (size_t)q * P.p_pad * KC, marker_chunk_bytes, &full[s], keep_policy);
     double* sc = st + (size_t)NQ * MT * KC;
     bulk_g2s(sc + TT, P.et + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
     if (HAS_E) bulk_g2s(sc, P.e + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
