@@ -1,23 +1,30 @@
 #!/usr/bin/env python
 """bench.py — marker x trait LOD tests/sec on the BXD-shape bulkscan (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload alt-grid|null-grid] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload alt-grid|null-grid|null-exact|scaled-null-exact|perms]
 
-One "step" = one full bulkscan call (rotation by U' -> per-trait null statistics over the h2 grid ->
-weight-folded marker operand -> fused DMMA scan with the LOD / max-over-grid epilogue) on synthetic
-BXD-shape data (n=79, p=7321 markers, m=35554 traits, 10-point h2 grid).  The kinship
-eigendecomposition is setup (one-off, timed separately and reported as `setup_ms`).
+One "step" = one full scan call through the C-ABI (rotation by U' -> per-trait null statistics / Brent
+fit -> marker operand -> fused DMMA scan with the LOD epilogue) on synthetic data:
 
-  value      : whole-job tests/s, inputs resident in HBM, outputs (L, h2_panel) left in HBM
+  alt-grid (default)  BASELINE.json configs[2], the north-star target: n=79, p=7321, m=35554, 10-point grid
+  null-grid           configs[1]: same shape, bulkscan default method (the reference's published 2.11 s)
+  null-exact          same shape, per-trait REML Brent + per-trait-weight scan (bulkscan_null)
+  scaled-null-exact   configs[4]: n=1000, p=100000, m=20000, c=3, REML
+  perms               configs[3]: scan, 1 trait x 10000 permutations x 7321 markers
+
+The kinship eigendecomposition is setup (one-off, timed separately and reported as `setup_ms`).
+
+  value      : whole-job tests/s, inputs resident in HBM, outputs left in HBM
   e2e        : the same call through the C-ABI with HOST (pinned) buffers: H2D of Y,G,Covar,U,lambda
-               and D2H of the p x m outputs inside the timed region
+               and D2H of the outputs inside the timed region
   roofline   : the fused scan kernel against the measured FP64 tensor peak (profiles/fp64_peak_r01.json)
   cpu_baseline: the CPU oracle (numpy restatement of the reference algorithm), all host cores, on a
-               bounded trait sample of the same workload
+               bounded sample of the same workload
 
-N > 1 (torchrun, one rank per GPU): traits are sharded across ranks (strong scaling: the BXD problem
-is fixed), G/U are replicated, there is no data-path collective; NCCL is used for the barrier and
-the max-over-ranks time.
+N > 1 (torchrun, one rank per GPU): traits (bulkscan) or permutations (scan) are sharded across ranks
+(strong scaling: the problem is fixed), G/U are replicated, there is no data-path collective; NCCL is
+used for the barrier and the max-over-ranks time.
 """
 from __future__ import annotations
 
@@ -35,17 +42,33 @@ for sub in ("bulklmm.jl_b200", "oracle"):
 
 import numpy as np  # noqa: E402
 
-N_BXD, P_BXD, M_BXD = 79, 7321, 35554
 GRID = np.arange(10) / 10.0  # 0.0:0.1:0.9, src/bulkscan.jl:82
 README_REF = {"value": 1.23e8, "what": "reference README.md:336-339: bulkscan null-grid, 2.112 s, 16 Julia threads, "
-                                       "48x Xeon Silver 4214 (other hardware; not this metric's alt-grid method)"}
+                                       "48x Xeon Silver 4214 (other hardware)"}
+METRIC = "marker x trait LOD tests/sec, BXD-shape bulkscan"
+
+# name -> shape, method, covariate columns (incl. intercept), opts, flops per test / n, outputs, cpu sample
+WORKLOADS = {
+    "alt-grid": dict(n=79, p=7321, m=35554, c=1, method="alt-grid", opts=dict(h2_grid=GRID), fmult=len(GRID),
+                     cfg="BASELINE.json configs[2]", outputs="L and h2_panel (p x m f64 each)", cpu_m=8192),
+    "null-grid": dict(n=79, p=7321, m=35554, c=1, method="null-grid", opts=dict(h2_grid=GRID), fmult=1,
+                      cfg="BASELINE.json configs[1]", outputs="L (p x m f64) and h2_null_list", cpu_m=35554),
+    "null-exact": dict(n=79, p=7321, m=35554, c=1, method="null-exact", opts=dict(reml=True, prior_variance=0.0),
+                       fmult=3, cfg="BXD shape, bulkscan_null", outputs="L (p x m f64) and h2_null_list", cpu_m=1024),
+    "scaled-null-exact": dict(n=1000, p=100000, m=20000, c=3, method="null-exact",
+                              opts=dict(reml=True, prior_variance=0.0), fmult=5, cfg="BASELINE.json configs[4]",
+                              outputs="L (p x m f64) and h2_null_list", cpu_m=16),
+    "perms": dict(n=79, p=7321, m=10001, c=1, method="perms", opts=dict(prior_variance=0.0), fmult=1,
+                  cfg="BASELINE.json configs[3]", outputs="lod, L_perms (p x nperms f64), per-permutation max", cpu_m=10000),
+}
 
 
 def fp64_peak():
     path = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return d["cublas_dgemm_tflops_sustained"], "measured: cuBLAS DGEMM 8192^3 sustained on this pool (profiles/fp64_peak_r01.json); MEASURED_PEAKS.json has no FP64 entry"
+        return d["cublas_dgemm_tflops_sustained"], ("measured: cuBLAS DGEMM 8192^3 sustained on this pool "
+                                                    "(profiles/fp64_peak_r01.json); MEASURED_PEAKS.json has no FP64 entry")
     return 37.0, "fallback: B200 datasheet FP64 tensor 37 TFLOP/s (no measured file)"
 
 
@@ -64,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -100,86 +123,110 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle, threaded over trait blocks like the reference (Threads.@threads over nb
-# blocks with BLAS pinned to one thread, src/bulkscan.jl:252-286)
+# synthetic inputs: same generator and seeds on every rank
 # ------------------------------------------------------------------------------------------------
-def cpu_scan(workload, Y, G, K, Ut, lam, cores):
+def make_inputs(w, m_limit=None, seed=0):
+    from blmm_b200 import synth
+    n, p, c = w["n"], w["p"], w["c"]
+    m = w["m"] if m_limit is None else min(m_limit, w["m"])
+    G = synth.make_geno(n, p, seed=p)
+    K = synth.calc_kinship_host(G)
+    if w["method"] == "perms":
+        Y = synth.make_pheno(G, K, 1112, seed=35554)[:, 1111:1112]  # trait column 1112
+    else:
+        Y = synth.make_pheno(G, K, m, seed=w["m"] + seed)
+    Cv = np.ones((n, 1)) if c == 1 else np.hstack([np.ones((n, 1)), synth.make_covar(n)[:, :c - 1]])
+    return Y, G, K, Cv
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle, threaded over trait blocks like the reference (Threads.@threads over nb blocks
+# with BLAS pinned to one thread, src/bulkscan.jl:252-286)
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(name, repeats=1, warmup=0):
+    """Time the oracle on a bounded sample of the workload (inputs generated once); returns the mean of
+    `repeats` timed runs after `warmup` untimed ones."""
     import blmm_oracle as orc
+    from blmm_b200 import synth
     from concurrent.futures import ThreadPoolExecutor
     try:
         from threadpoolctl import threadpool_limits
     except Exception:  # pragma: no cover
         threadpool_limits = None
-    m = Y.shape[1]
-    nb = max(1, min(cores * 2, m // 64))
-    edges = np.linspace(0, m, nb + 1).astype(int)
-    fn = orc.bulkscan_alt_grid if workload == "alt-grid" else orc.bulkscan_null_grid
-
-    def work(i):
-        return fn(Y[:, edges[i]:edges[i + 1]], G, K, GRID, Ut=Ut, lam=lam)
-
-    def run():
-        with ThreadPoolExecutor(cores) as ex:
-            return list(ex.map(work, range(nb)))
-
-    t0 = time.perf_counter()
-    if threadpool_limits is not None:
-        with threadpool_limits(limits=1):
-            run()
-    else:
-        run()
-    return time.perf_counter() - t0
-
-
-def cpu_baseline(workload, sample_m, seed=0):
-    import blmm_oracle as orc
-    from blmm_b200 import synth
+    w = WORKLOADS[name]
     cores = os.cpu_count() or 1
-    G = synth.make_geno(N_BXD, P_BXD)
-    K = synth.calc_kinship_host(G)
-    Y = synth.make_pheno(G, K, sample_m, seed=35554 + seed)
+    sample_m = w["cpu_m"]
+    Y, G, K, Cv = make_inputs(w, m_limit=sample_m)
+    n, p = G.shape
     Ut, lam = orc.decompose(K)
-    dt = cpu_scan(workload, Y, G, K, Ut, lam, cores)
-    return {"value": P_BXD * sample_m / dt, "unit": "tests/s", "cores": cores, "kind": "port",
-            "sample": f"{workload}, all {P_BXD} markers x first {sample_m} of {M_BXD} synthetic BXD-shape traits, "
-                      f"{len(GRID)}-point grid, {dt:.2f} s; numpy oracle threaded over trait blocks "
-                      f"(reference cannot run: no Julia in the image)",
+    covar = None if w["c"] == 1 else Cv[:, 1:]
+    if w["method"] == "perms":
+        perm = synth.make_perm_indices(n, sample_m, 0)
+        run = lambda: orc.scan(Y, G, K, permutation_test=True, perm_idx=perm, Ut=Ut, lam=lam)  # BLAS-threaded GEMM
+        tests = p * (sample_m + 1)
+        what = f"{sample_m} of 10000 permutations, OpenBLAS threads"
+    else:
+        nb = max(1, min(cores * 2, sample_m // 4))
+        edges = np.linspace(0, sample_m, nb + 1).astype(int)
+        if w["method"] == "alt-grid":
+            fn = lambda Ys: orc.bulkscan_alt_grid(Ys, G, K, GRID, Covar=covar, Ut=Ut, lam=lam)
+        elif w["method"] == "null-grid":
+            fn = lambda Ys: orc.bulkscan_null_grid(Ys, G, K, GRID, Covar=covar, Ut=Ut, lam=lam)
+        else:
+            fn = lambda Ys: orc.bulkscan_null(Ys, G, K, Covar=covar, reml=True, prior_variance=0.0, Ut=Ut, lam=lam)
+
+        def pool():
+            with ThreadPoolExecutor(cores) as ex:
+                return list(ex.map(lambda i: fn(Y[:, edges[i]:edges[i + 1]]), range(nb)))
+
+        def run():
+            if threadpool_limits is not None:
+                with threadpool_limits(limits=1):
+                    pool()
+            else:
+                pool()
+
+        tests = p * sample_m
+        what = f"first {sample_m} of {w['m']} synthetic traits, threaded over {nb} trait blocks"
+    times = []
+    for i in range(warmup + repeats):
+        t0 = time.perf_counter()
+        run()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    return {"value": tests / dt, "unit": "tests/s", "cores": cores, "kind": "port",
+            "sample": f"{name}, all {p} markers x {what}, {dt:.2f} s per run; numpy oracle (CPU restatement of the "
+                      f"reference algorithm; the Julia reference cannot run: no Julia in the image)",
             "seconds": dt}
 
 
+def workload_config(name, gpus):
+    w = WORKLOADS[name]
+    unit = "permutations" if w["method"] == "perms" else "traits"
+    return {"workload": f"{'scan with permutations' if w['method'] == 'perms' else 'bulkscan ' + w['method']}, "
+                        f"n={w['n']} p={w['p']} {'nperms+1' if w['method'] == 'perms' else 'm'}={w['m']}, c={w['c']}"
+                        f"{', h2 grid 0:0.1:0.9, ML' if 'grid' in w['method'] else ''} ({w['cfg']})",
+            "n": w["n"], "p": w["p"], "m": w["m"], "c": w["c"], "outputs": w["outputs"],
+            "sharding": f"{unit} over {gpus} GPU(s), G/U replicated, no data-path collective",
+            "l2": "explicit 512 MB L2 flush between timed steps (each step also writes > L2 of output)"}
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port (Julia is
-    not installed, so oracle/_ref does not exist), all host cores, bounded sample per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (Julia is not
+    installed, so oracle/_ref does not exist), all host cores, bounded sample per step."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    sample_m = 2048 if args.workload == "alt-grid" else 8192
-    times = []
-    last = None
-    for i in range(args.warmup + args.steps):
-        last = cpu_baseline(args.workload, sample_m, seed=i)
-        if i >= args.warmup:
-            times.append(last["seconds"])
-    dt = float(np.mean(times))
-    value = P_BXD * sample_m / dt
-    line = {"impl": "reference", "metric": "marker x trait LOD tests/sec, BXD-shape bulkscan", "value": value,
-            "unit": "tests/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+    last = cpu_baseline(args.workload, repeats=args.steps, warmup=args.warmup)
+    dt, value = last["seconds"], last["value"]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "tests/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, args.gpus),
             "cpu_baseline": {"value": value, "unit": "tests/s", "cores": last["cores"], "kind": "port",
                              "sample": last["sample"]},
             "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def workload_config(workload, gpus):
-    return {"workload": f"bulkscan {workload}, BXD shape n={N_BXD} p={P_BXD} m={M_BXD}, h2 grid 0:0.1:0.9, ML, "
-                        f"c=1 (BASELINE.json configs[{2 if workload == 'alt-grid' else 1}])",
-            "n": N_BXD, "p": P_BXD, "m": M_BXD, "ngrid": len(GRID), "outputs": "L and h2_panel (p x m f64 each)"
-            if workload == "alt-grid" else "L (p x m f64) and h2_null_list",
-            "sharding": f"traits over {gpus} GPU(s), G/U replicated, no data-path collective",
-            "l2": "explicit 512 MB L2 flush between timed steps (each step also writes > 2 GB of output)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -189,7 +236,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="alt-grid", choices=["alt-grid", "null-grid"])
+    ap.add_argument("--workload", default="alt-grid", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg")
     ap.add_argument("--no-other", action="store_true", help="skip the short runs of the other configs")
@@ -211,43 +258,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
-
-    # ---- synthetic inputs: same generator and seeds on every rank, then shard traits
-    n, p, m = N_BXD, P_BXD, M_BXD
-    G = synth.make_geno(n, p)
-    K = synth.calc_kinship_host(G)
-    Y = synth.make_pheno(G, K, m)
-    j0, j1 = rank * m // world, (rank + 1) * m // world
-    Ysh = np.asfortranarray(Y[:, j0:j1])
-    ml = j1 - j0
-    Cv = np.ones((n, 1))
+    METHODS = {"alt-grid": L.METHOD_ALT_GRID, "null-grid": L.METHOD_NULL_GRID, "null-exact": L.METHOD_NULL_EXACT,
+               "perms": L.METHOD_NULL_EXACT}
 
     eng = Engine(local)
-    t0 = time.perf_counter()
-    U, lam, _ = eng.decompose(K)  # setup: cuSOLVER syevd
-    setup_ms = (time.perf_counter() - t0) * 1e3
-    t0 = time.perf_counter()
-    eng.decompose(K)
-    setup_ms_warm = (time.perf_counter() - t0) * 1e3
-
-    method = L.METHOD_ALT_GRID if args.workload == "alt-grid" else L.METHOD_NULL_GRID
-    alt = args.workload == "alt-grid"
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+    eng.set_profiling(True)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def colmajor(a):
         return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).T))
-
-    hY, hG, hC, hU, hl = colmajor(Ysh), colmajor(G), colmajor(Cv), colmajor(U), torch.from_numpy(lam.copy())
-    dY, dG, dC, dU, dl = (t.to(dev) for t in (hY, hG, hC, hU, hl))
-    dL = torch.empty((ml, p), dtype=torch.float64, device=dev)
-    dH = torch.empty((ml, p), dtype=torch.float64, device=dev) if alt else torch.empty(ml, dtype=torch.float64, device=dev)
-    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    pr = eng.make_problem(n, p, ml, 1, dY.data_ptr(), dG.data_ptr(), dC.data_ptr(), dU.data_ptr(), dl.data_ptr())
-    opts, keep = eng.make_opts(method=method, h2_grid=GRID, mem_space=L.MEM_DEVICE)
-    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
-    eng.set_profiling(True)
-
-    def step():
-        eng.bulkscan_raw(pr, opts, dL.data_ptr(), dH.data_ptr())
 
     def barrier():
         if world > 1:
@@ -255,144 +275,173 @@ def main():
         torch.cuda.synchronize(dev)
         eng.sync()
 
-    for _ in range(args.warmup):
-        step()
-        eng.sync()
+    class Job:
+        """One workload resident on this rank's GPU: step() = one C-ABI call with device pointers."""
+
+        def __init__(self, name, decomposition=None):
+            w = self.w = WORKLOADS[name]
+            self.name = name
+            n, p, c = w["n"], w["p"], w["c"]
+            Y, G, K, Cv = make_inputs(w)
+            self.K = K
+            self.perms = w["method"] == "perms"
+            t0 = time.perf_counter()
+            U, lam, _ = eng.decompose(K)  # setup: cuSOLVER syevd
+            self.setup_ms = (time.perf_counter() - t0) * 1e3
+            cols = w["m"] - 1 if self.perms else w["m"]  # sharded units: traits or permutations
+            j0, j1 = rank * cols // world, (rank + 1) * cols // world
+            self.ml = ml = j1 - j0
+            self.tests_local = p * (ml + (1 if self.perms and rank == 0 else 0))
+            self.tests_total = p * w["m"]
+            self.h = [colmajor(Y if self.perms else Y[:, j0:j1]), colmajor(G), colmajor(Cv), colmajor(U),
+                      torch.from_numpy(lam.copy())]
+            self.d = [t.to(dev) for t in self.h]
+            self.method = METHODS[w["method"]]
+            alt = w["method"] == "alt-grid"
+            self.out_shapes = [(ml, p), (ml, p) if alt else (ml,)]
+            if self.perms:
+                idx = synth.make_perm_indices(n, cols, 0)[:, j0:j1]
+                self.hperm = torch.from_numpy(np.ascontiguousarray(idx.T))
+                self.dperm = self.hperm.to(dev)
+                self.out_shapes = [(ml, p), (ml,), (p,), (2,)]  # L_perms, max, lod, (sigma2, h2)
+            self.dout = [torch.empty(s, dtype=torch.float64, device=dev) for s in self.out_shapes]
+            self.opts, self._keep = eng.make_opts(method=self.method, mem_space=L.MEM_DEVICE, **w["opts"])
+            self.pr = eng.make_problem(n, p, 1 if self.perms else ml, c, *[t.data_ptr() for t in self.d])
+            self.flops = 2.0 * n * p * (ml + (1 if self.perms else 0)) * w["fmult"]
+            self.out_bytes = 8.0 * sum(int(np.prod(s)) for s in self.out_shapes[:2])
+
+        def call(self, pr, opts, outs, perm):
+            if self.perms:
+                eng.scan_perms_raw(pr, opts, perm.data_ptr(), self.ml, outs[2].data_ptr(), outs[0].data_ptr(),
+                                   outs[1].data_ptr(), outs[3].data_ptr(), outs[3].data_ptr() + 8)
+            else:
+                eng.bulkscan_raw(pr, opts, outs[0].data_ptr(), outs[1].data_ptr())
+
+        def step(self):
+            self.call(self.pr, self.opts, self.dout, getattr(self, "dperm", None))
+
+        def timed(self, steps, warmup):
+            for _ in range(warmup):
+                self.step()
+                eng.sync()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            scan_ms = []
+            barrier()
+            l0, w0 = eng.launch_count, time.time()
+            for a, b in evs:
+                with torch.cuda.stream(stream):
+                    flush.zero_()  # L2 flush, outside the step's event pair
+                a.record(stream)
+                self.step()
+                b.record(stream)
+                eng.sync()
+                scan_ms.append(eng.last_scan_ms())
+            barrier()
+            w1 = time.time()
+            total_ms = sum(a.elapsed_time(b) for a, b in evs)
+            local_ms = total_ms
+            if world > 1:
+                tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                total_ms = float(tt.item())
+            return dict(total_ms=total_ms, local_ms=local_ms, scan_ms=float(np.mean(scan_ms)),
+                        launches=eng.launch_count - l0, wall=(w0, w1))
+
+        def e2e(self, steps):
+            """host (pinned) buffers through the C-ABI, H2D + D2H inside the timed region"""
+            w = self.w
+            pin = [t.pin_memory() for t in self.h]
+            pout = [torch.empty(s, dtype=torch.float64).pin_memory() for s in self.out_shapes]
+            pperm = self.hperm.pin_memory() if self.perms else None
+            hpr = eng.make_problem(w["n"], w["p"], 1 if self.perms else self.ml, w["c"], *[t.data_ptr() for t in pin])
+            hopts, keep2 = eng.make_opts(method=self.method, mem_space=L.MEM_HOST, **w["opts"])
+            self.call(hpr, hopts, pout, pperm)  # warm (allocates staging)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                self.call(hpr, hopts, pout, pperm)  # blocking: returns with results on the host
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            h2d = sum(t.numel() * t.element_size() for t in pin) + (pperm.numel() * 4 if self.perms else 0)
+            d2h = sum(t.numel() * 8 for t in pout)
+            assert torch.equal(pout[0], self.dout[0].cpu()), "host-buffer result differs from device-resident result"
+            return {"value": self.tests_total * steps / dt, "unit": "tests/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / steps * 1e3, "steps": steps,
+                    "note": "per rank bytes; pinned host buffers; wall clock around blocking C-ABI calls; the "
+                            "alt-grid copy-back overlaps the scan (trait-tile chunks on a second stream)"}
+
+    job = Job(args.workload)
+    w = job.w
+    t0 = time.perf_counter()
+    eng.decompose(job.K)
+    setup_ms_warm = (time.perf_counter() - t0) * 1e3
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    scan_ms = []
-    barrier()
-    launches0 = eng.launch_count
-    wall0 = time.time()
-    for a, b in evs:
-        with torch.cuda.stream(stream):
-            flush.zero_()  # L2 flush, outside the step's event pair
-        a.record(stream)
-        step()
-        b.record(stream)
-        eng.sync()
-        scan_ms.append(eng.last_scan_ms())
-    barrier()
-    wall1 = time.time()
-    launches = eng.launch_count - launches0
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    if world > 1:
-        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
-    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    value = p * m * args.steps / (total_ms * 1e-3)
+    r = job.timed(args.steps, args.warmup)
+    clocks = sampler.stop(*r["wall"]) if rank == 0 else None
+    value = job.tests_total * args.steps / (r["total_ms"] * 1e-3)
 
-    # ---- roofline of the dominant kernel (the fused scan), measured live with CUDA events
-    ngrid = len(GRID)
-    flops = 2.0 * n * p * ml * (ngrid if alt else 1)
-    scan_avg_ms = float(np.mean(scan_ms))
+    # ---- roofline of the dominant kernel (the fused scan), measured live with CUDA events inside the library
     peak, peak_src = fp64_peak()
-    out_bytes = 8.0 * p * ml * (2 if alt else 1)
     hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    t_tensor = flops / (peak * 1e12)
-    t_hbm = out_bytes / (hbm * 1e9)
-    ach = flops / (scan_avg_ms * 1e-3) / 1e12
+    t_tensor = job.flops / (peak * 1e12)
+    t_hbm = job.out_bytes / (hbm * 1e9)
+    ach = job.flops / (r["scan_ms"] * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "scan_traffic_r01.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
         traffic = json.load(open(tpath)).get(args.workload)
+    kname = ("blmm::scan_stream_kernel (FP64 DMMA.8x8x4, K-streamed TMA bulk copies)" if "exact" in args.workload
+             else "blmm::scan_kernel (FP64 DMMA.8x8x4, TMA bulk copies)")
     roofline = {"bound": "tensor" if t_tensor >= t_hbm else "hbm", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": traffic, "kernel": "blmm::scan_kernel (FP64 DMMA.8x8x4, TMA bulk copies)",
-                "kernel_ms": scan_avg_ms, "kernel_share_of_step": scan_avg_ms * args.steps / sum(a.elapsed_time(b) for a, b in evs),
-                "algorithmic_flops_per_launch": flops, "algorithmic_output_bytes_per_launch": out_bytes,
-                "t_roof_ms": max(t_tensor, t_hbm) * 1e3, "frac_of_t_roof": max(t_tensor, t_hbm) * 1e3 / scan_avg_ms,
+                "frac": ach / peak, "traffic": traffic, "kernel": kname, "kernel_ms": r["scan_ms"],
+                "kernel_share_of_step": r["scan_ms"] * args.steps / r["local_ms"],
+                "algorithmic_flops_per_launch": job.flops, "algorithmic_output_bytes_per_launch": job.out_bytes,
+                "t_roof_ms": max(t_tensor, t_hbm) * 1e3, "frac_of_t_roof": max(t_tensor, t_hbm) * 1e3 / r["scan_ms"],
                 "peak_source": peak_src, "hbm_gbs": hbm}
 
-    # ---- e2e: host (pinned) buffers through the C-ABI, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        pin = lambda t: t.pin_memory()
-        pY, pG, pC, pU, pl = pin(hY), pin(hG), pin(hC), pin(hU), pin(hl)
-        pL = torch.empty((ml, p), dtype=torch.float64).pin_memory()
-        pH = (torch.empty((ml, p), dtype=torch.float64) if alt else torch.empty(ml, dtype=torch.float64)).pin_memory()
-        hpr = eng.make_problem(n, p, ml, 1, pY.data_ptr(), pG.data_ptr(), pC.data_ptr(), pU.data_ptr(), pl.data_ptr())
-        hopts, keep2 = eng.make_opts(method=method, h2_grid=GRID, mem_space=L.MEM_HOST)
-        e2e_steps = max(2, min(args.steps, 5))
-        eng.bulkscan_raw(hpr, hopts, pL.data_ptr(), pH.data_ptr())  # warm (allocates staging)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            eng.bulkscan_raw(hpr, hopts, pL.data_ptr(), pH.data_ptr())  # blocking: returns with results on the host
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-        h2d = sum(t.numel() * t.element_size() for t in (pY, pG, pC, pU, pl))
-        d2h = pL.numel() * 8 + pH.numel() * 8
-        e2e = {"value": p * m * e2e_steps / dt, "unit": "tests/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": dt / e2e_steps * 1e3, "steps": e2e_steps,
-               "note": "per rank bytes; pinned host buffers; wall clock around blocking C-ABI calls"}
-        # sanity: host and device paths agree
-        assert torch.equal(pL, dL.cpu()), "host-buffer result differs from device-resident result"
+        try:
+            e2e = job.e2e(max(2, min(args.steps, 5)))
+        except RuntimeError as ex:  # pinned allocation of a very large result can fail on small hosts
+            e2e = {"value": None, "unit": "tests/s", "error": str(ex)[:200]}
 
     # ---- the other BASELINE.json configs on one GPU, device-resident, a few steps each (context for the
     # headline number, not part of it)
     other = None
-    if world == 1 and not args.no_other:
+    if world == 1 and not args.no_other and args.workload == "alt-grid":
         other = {}
-
-        def timed(fn, reps=3):
-            fn(); eng.sync()
-            ms, ks = [], []
-            for _ in range(reps):
-                with torch.cuda.stream(stream):
-                    flush.zero_()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream); fn(); b.record(stream); eng.sync()
-                ms.append(a.elapsed_time(b)); ks.append(eng.last_scan_ms())
-            return float(np.mean(ms)), float(np.mean(ks))
-
-        dh = torch.empty(ml, dtype=torch.float64, device=dev)
-        for name, meth, kw, fl in (("null-grid", L.METHOD_NULL_GRID, dict(h2_grid=GRID), 2.0 * n * p * ml),
-                                   ("null-exact (REML Brent per trait)", L.METHOD_NULL_EXACT, dict(reml=True, prior_variance=0.0),
-                                    2.0 * n * p * ml * 3)):
-            if alt is False and name == "null-grid":
-                continue
-            o2, keep3 = eng.make_opts(method=meth, mem_space=L.MEM_DEVICE, **kw)
-            t_ms, k_ms = timed(lambda: eng.bulkscan_raw(pr, o2, dL.data_ptr(), dh.data_ptr()))
-            other[name] = {"ms_per_step": t_ms, "tests_per_s": p * ml / (t_ms * 1e-3), "scan_kernel_ms": k_ms,
-                           "scan_kernel_tflops": fl / (k_ms * 1e-3) / 1e12}
-        nperms = 10000
-        perm = torch.from_numpy(np.ascontiguousarray(synth.make_perm_indices(n, nperms, 0).T)).to(dev)
-        dy1 = dY[1111:1112].contiguous()
-        pr1 = eng.make_problem(n, p, 1, 1, dy1.data_ptr(), dG.data_ptr(), dC.data_ptr(), dU.data_ptr(), dl.data_ptr())
-        o3, _k = eng.make_opts(method=L.METHOD_NULL_EXACT, prior_variance=0.0, mem_space=L.MEM_DEVICE)
-        lod1 = torch.empty(p, dtype=torch.float64, device=dev)
-        mx = torch.empty(nperms, dtype=torch.float64, device=dev)
-        sc = torch.empty(2, dtype=torch.float64, device=dev)
-        for name, lp in (("scan 1 trait x 10000 permutations, per-permutation max only", None),
-                         ("scan 1 trait x 10000 permutations, L_perms materialised", dL.data_ptr())):
-            t_ms, k_ms = timed(lambda: eng.scan_perms_raw(pr1, o3, perm.data_ptr(), nperms, lod1.data_ptr(), lp,
-                                                          mx.data_ptr(), sc.data_ptr(), sc.data_ptr() + 8))
-            other[name] = {"ms_per_step": t_ms, "tests_per_s": p * (nperms + 1) / (t_ms * 1e-3), "scan_kernel_ms": k_ms,
-                           "scan_kernel_tflops": 2.0 * n * p * (nperms + 1) / (k_ms * 1e-3) / 1e12}
+        del job.dout
+        for nm in ("null-grid", "null-exact", "perms"):
+            j2 = Job(nm)
+            r2 = j2.timed(5, 2)
+            other[nm] = {"workload": workload_config(nm, 1)["workload"], "ms_per_step": r2["total_ms"] / 5,
+                         "tests_per_s": j2.tests_total * 5 / (r2["total_ms"] * 1e-3), "scan_kernel_ms": r2["scan_ms"],
+                         "scan_kernel_tflops": j2.flops / (r2["scan_ms"] * 1e-3) / 1e12}
+            del j2
 
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:
-        cpu = cpu_baseline(args.workload, 2048 if alt else 8192)
+        cpu = cpu_baseline(args.workload)
         cpu.pop("seconds", None)
 
     if rank == 0:
-        line = {"metric": "marker x trait LOD tests/sec, BXD-shape bulkscan", "value": value, "unit": "tests/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": workload_config(args.workload, world), "roofline": roofline,
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "other_workloads": other,
-                "setup_ms": {"eigendecomposition_first_call": setup_ms, "eigendecomposition_warm": setup_ms_warm},
+        vs = value / README_REF["value"] if args.workload == "null-grid" else None
+        line = {"metric": METRIC, "value": value, "unit": "tests/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["total_ms"] / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": vs, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args.workload, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(r["launches"]), "clocks": clocks, "other_workloads": other,
+                "setup_ms": {"eigendecomposition_first_call": job.setup_ms, "eigendecomposition_warm": setup_ms_warm},
                 "reference_published": README_REF}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -14,6 +14,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 METHOD_NULL_GRID, METHOD_ALT_GRID, METHOD_NULL_EXACT = 0, 1, 2
 H2PANEL_REFERENCE, H2PANEL_ARGMAX = 0, 1
 DECOMP_EIGEN, DECOMP_SVD = 0, 1
+ABI_VERSION = 2
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -22,14 +23,15 @@ c_int32_p = C.POINTER(C.c_int32)
 class Problem(C.Structure):
     _fields_ = [("n", C.c_int64), ("p", C.c_int64), ("m", C.c_int64), ("c", C.c_int64),
                 ("Y", C.c_void_p), ("G", C.c_void_p), ("Covar", C.c_void_p), ("U", C.c_void_p),
-                ("lam", C.c_void_p)]
+                ("lam", C.c_void_p), ("obs_weights", C.c_void_p)]
 
 
 class Opts(C.Structure):
     _fields_ = [("method", C.c_int32), ("reml", C.c_int32), ("prior_variance", C.c_double),
                 ("prior_sample_size", C.c_double), ("h2_grid", c_double_p), ("ngrid", C.c_int32),
                 ("optim_interval", C.c_int32), ("h2_panel_mode", C.c_int32), ("mem_space", C.c_int32),
-                ("ld_out", C.c_int64)]
+                ("ld_out", C.c_int64), ("chisq_df", C.c_int32), ("reserved", C.c_int32),
+                ("log10p_out", C.c_void_p)]
 
 
 # every symbol include/blmm_b200.h declares: name -> (restype, argtypes)
@@ -55,6 +57,10 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "blmm_scan_null": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.POINTER(Opts), C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "blmm_lod2log10p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                  C.c_void_p, C.c_int]),
+    "blmm_thresholds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "blmm_weight_kinship": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
 }
 
 _lib = None
@@ -74,7 +80,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.blmm_abi_version() != 1:
+    if lib.blmm_abi_version() != ABI_VERSION:
         raise RuntimeError("libblmm_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -93,7 +93,7 @@ class Engine:
     @staticmethod
     def make_opts(method=L.METHOD_NULL_GRID, reml=False, prior_variance=1.0, prior_sample_size=0.0,
                   h2_grid=None, optim_interval=1, h2_panel_mode=L.H2PANEL_REFERENCE, mem_space=L.MEM_HOST,
-                  ld_out=0):
+                  ld_out=0, chisq_df=0, log10p_out=None):
         o = L.Opts()
         o.method = method
         o.reml = int(bool(reml))
@@ -108,23 +108,27 @@ class Engine:
         o.h2_panel_mode = h2_panel_mode
         o.mem_space = mem_space
         o.ld_out = ld_out
+        o.chisq_df = int(chisq_df)
+        o.log10p_out = log10p_out
         return o, keep
 
     @staticmethod
-    def make_problem(n, p, m, c, Y, G, Covar, U, lam):
+    def make_problem(n, p, m, c, Y, G, Covar, U, lam, obs_weights=None):
         """Raw-pointer problem (ints are addresses: host numpy `.ctypes.data` or device `data_ptr()`)."""
         pr = L.Problem()
         pr.n, pr.p, pr.m, pr.c = n, p, m, c
         pr.Y, pr.G, pr.Covar, pr.U, pr.lam = Y, G, Covar, U, lam
+        pr.obs_weights = obs_weights
         return pr
 
-    def _host_problem(self, Y, G, Covar, U, lam):
+    def _host_problem(self, Y, G, Covar, U, lam, weights=None):
         n = Covar.shape[0]
         m = 0 if Y is None else Y.shape[1]
         p = 0 if G is None else G.shape[1]
         pr = self.make_problem(n, p, m, Covar.shape[1],
                                None if Y is None else Y.ctypes.data, None if G is None else G.ctypes.data,
-                               Covar.ctypes.data, U.ctypes.data, lam.ctypes.data)
+                               Covar.ctypes.data, U.ctypes.data, lam.ctypes.data,
+                               None if weights is None else weights.ctypes.data)
         return pr
 
     # -- setup ---------------------------------------------------------------------------------
@@ -134,6 +138,33 @@ class Engine:
         K = np.empty((n, n), order="F")
         self._check(self.lib.blmm_kinship(self.h, n, p, _ptr(G), _ptr(K), L.MEM_HOST))
         return K
+
+    def weight_kinship(self, K, weights) -> np.ndarray:
+        """W*K*W (src/bulkscan.jl:239)."""
+        K, w = _f(K), np.ascontiguousarray(weights, dtype=np.float64)
+        n = K.shape[0]
+        if K.shape[1] != n or w.shape != (n,):
+            raise BlmmError(L.E_DIM, "Dimension mismatch.")
+        out = np.empty((n, n), order="F")
+        self._check(self.lib.blmm_weight_kinship(self.h, n, _ptr(K), _ptr(w), _ptr(out), L.MEM_HOST))
+        return out
+
+    def lod2log10p(self, lod, df: int = 1) -> np.ndarray:
+        """src/util.jl:199-206 elementwise on the device."""
+        a = _f(np.atleast_2d(np.asarray(lod, dtype=np.float64).T).T) if np.ndim(lod) < 2 else _f(lod)
+        out = np.empty_like(a, order="F")
+        self._check(self.lib.blmm_lod2log10p(self.h, _ptr(a), a.shape[0], a.shape[1], 0, 0, int(df), _ptr(out),
+                                             L.MEM_HOST))
+        return out.reshape(np.shape(lod))
+
+    def thresholds(self, max_lod, signif_level) -> np.ndarray:
+        """Type-7 quantiles of the per-permutation maximum LODs at 1 - signif_level (device sort)."""
+        mx = np.ascontiguousarray(max_lod, dtype=np.float64)
+        sl = np.ascontiguousarray(signif_level, dtype=np.float64)
+        thr = np.empty(sl.shape[0])
+        self._check(self.lib.blmm_thresholds(self.h, _ptr(mx), mx.shape[0], _ptr(sl), sl.shape[0], _ptr(thr),
+                                             L.MEM_HOST))
+        return thr
 
     def decompose(self, K, decomp_scheme: str = "eigen"):
         """(U, lambda): columns of U are eigenvectors (Ut = U.T).  Returns also #eigenvalues < -1e-7."""
@@ -174,21 +205,26 @@ class Engine:
 
     # -- the hot path (host buffers) -----------------------------------------------------------
     def bulkscan_host(self, Y, G, Covar, U, lam, method, h2_grid, reml, prior_variance, prior_sample_size,
-                      optim_interval=1, h2_panel_mode=L.H2PANEL_REFERENCE, want_h2=True):
+                      optim_interval=1, h2_panel_mode=L.H2PANEL_REFERENCE, want_h2=True, weights=None,
+                      chisq_df=0):
+        """Returns (L, h2) or, with chisq_df > 0, (L, h2, log10p)."""
         Y, G, Covar, U = _f(Y), _f(G), _f(Covar), _f(U)
         lam = np.ascontiguousarray(lam, dtype=np.float64)
+        weights = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
         p, m = G.shape[1], Y.shape[1]
-        pr = self._host_problem(Y, G, Covar, U, lam)
+        pr = self._host_problem(Y, G, Covar, U, lam, weights)
+        P = np.empty((p, m), order="F") if chisq_df else None
         o, keep = self.make_opts(method=method, reml=reml, prior_variance=prior_variance,
                                  prior_sample_size=prior_sample_size, h2_grid=h2_grid,
-                                 optim_interval=optim_interval, h2_panel_mode=h2_panel_mode)
+                                 optim_interval=optim_interval, h2_panel_mode=h2_panel_mode, chisq_df=chisq_df,
+                                 log10p_out=None if P is None else P.ctypes.data)
         Lout = np.empty((p, m), order="F")
         if method == L.METHOD_ALT_GRID:
             H = np.empty((p, m), order="F") if want_h2 else None
         else:
             H = np.empty(m) if want_h2 else None
         self._check(self.lib.blmm_bulkscan(self.h, C.byref(pr), C.byref(o), _ptr(Lout), _ptr(H)))
-        return Lout, H
+        return (Lout, H, P) if chisq_df else (Lout, H)
 
     def grid_loglik(self, Y, Covar, U, lam, h2_grid, reml=False, prior_variance=1.0, prior_sample_size=0.0):
         Y, Covar, U = _f(Y), _f(Covar), _f(U)
@@ -212,12 +248,13 @@ class Engine:
         return h2, s2, ell
 
     def scan_null_host(self, Y, G, Covar, U, lam, reml=False, prior_variance=0.0, prior_sample_size=0.0,
-                       optim_interval=1):
+                       optim_interval=1, weights=None):
         """blmm_scan_null: per-trait fitlmm + single-trait null scan for every column of Y."""
         Y, G, Covar, U = _f(Y), _f(G), _f(Covar), _f(U)
         lam = np.ascontiguousarray(lam, dtype=np.float64)
         p, m = G.shape[1], Y.shape[1]
-        pr = self._host_problem(Y, G, Covar, U, lam)
+        weights = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        pr = self._host_problem(Y, G, Covar, U, lam, weights)
         o, _ = self.make_opts(method=L.METHOD_NULL_EXACT, reml=reml, prior_variance=prior_variance,
                               prior_sample_size=prior_sample_size, optim_interval=optim_interval)
         lod = np.empty((p, m), order="F")
@@ -226,7 +263,7 @@ class Engine:
         return lod, s2, h2
 
     def scan_perms_host(self, y, G, Covar, U, lam, perm_idx, reml=False, prior_variance=0.0,
-                        prior_sample_size=0.0, optim_interval=1, want_L=True, want_max=True):
+                        prior_sample_size=0.0, optim_interval=1, want_L=True, want_max=True, weights=None):
         y, G, Covar, U = _f(y), _f(G), _f(Covar), _f(U)
         lam = np.ascontiguousarray(lam, dtype=np.float64)
         perm_idx = np.asfortranarray(np.asarray(perm_idx, dtype=np.int32))
@@ -234,7 +271,8 @@ class Engine:
         if perm_idx.ndim != 2 or (perm_idx.shape[1] > 0 and perm_idx.shape[0] != n):
             raise BlmmError(L.E_DIM, "Dimension mismatch.")
         nperms = perm_idx.shape[1]
-        pr = self._host_problem(y, G, Covar, U, lam)
+        weights = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        pr = self._host_problem(y, G, Covar, U, lam, weights)
         o, _ = self.make_opts(reml=reml, prior_variance=prior_variance, prior_sample_size=prior_sample_size,
                               optim_interval=optim_interval)
         lod = np.empty(p)
@@ -278,10 +316,12 @@ def transform_rotation(y, g, K, addIntercept: bool = True, decomp_scheme: str = 
     return Y0, X0, lam
 
 
-def _prep(Y, G, Covar, K, weights, addIntercept):
-    """The argument plumbing shared by the bulkscan methods: default intercept-only covariates
-    (3-argument forms, src/bulkscan.jl:94-109), intercept column, and the observation-weight
-    pre-scaling block (src/bulkscan.jl:231-250, 351-370, 457-476)."""
+def _prep(Y, G, Covar, K, weights, addIntercept, eng):
+    """The argument plumbing shared by the scan entry points: default intercept-only covariates
+    (3-argument forms, src/bulkscan.jl:94-109) and the intercept column.  Observation weights
+    (src/bulkscan.jl:231-250, 351-370, 457-476) are NOT applied here: they cross the ABI
+    (blmm_problem.obs_weights) and Y, G, Covar are row-scaled on the device; only the n x n kinship is
+    turned into W*K*W up front (blmm_weight_kinship) because it feeds the decomposition."""
     Y = np.asarray(Y, dtype=np.float64)
     if Y.ndim == 1:
         Y = Y.reshape(-1, 1)
@@ -296,12 +336,11 @@ def _prep(Y, G, Covar, K, weights, addIntercept):
         Covar = np.asarray(Covar, dtype=np.float64).reshape(n, -1)
         C0 = np.hstack([np.ones((n, 1)), Covar]) if addIntercept else Covar
     if weights is not None:
-        W = np.asarray(weights, dtype=np.float64)
-        Y = W[:, None] * Y
-        G = W[:, None] * G
-        C0 = W[:, None] * C0
-        K = W[:, None] * K * W[None, :]
-    return Y, G, C0, K
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        if weights.shape != (n,):
+            raise BlmmError(L.E_DIM, "Dimension mismatch.")
+        K = eng.weight_kinship(K, weights)
+    return Y, G, C0, K, weights
 
 
 _METHODS = {"null-grid": L.METHOD_NULL_GRID, "alt-grid": L.METHOD_ALT_GRID, "null-exact": L.METHOD_NULL_EXACT}
@@ -319,21 +358,23 @@ def bulkscan(Y, G, K, Covar=None, method: str = "null-grid", h2_grid=None, nb: i
         raise BlmmError(L.E_INVALID, "unknown method: choose null-exact, null-grid or alt-grid")
     if h2_grid is None:
         h2_grid = np.arange(10) / 10.0  # collect(0.0:0.1:0.9), src/bulkscan.jl:82
-    Y, G, C0, K = _prep(Y, G, Covar, K, weights, addIntercept)
+    Y, G, C0, K, weights = _prep(Y, G, Covar, K, weights, addIntercept, eng)
     if decomposition is None:
         U, lam, _ = eng.decompose(K, decomp_scheme)
     else:
         U, lam = decomposition
     mode = L.H2PANEL_ARGMAX if h2_panel_mode == "argmax" else L.H2PANEL_REFERENCE
-    Lmat, H = eng.bulkscan_host(Y, G, C0, U, lam, _METHODS[method], h2_grid, reml, prior_variance,
-                                prior_sample_size, optim_interval=optim_interval, h2_panel_mode=mode)
+    res = eng.bulkscan_host(Y, G, C0, U, lam, _METHODS[method], h2_grid, reml, prior_variance,
+                            prior_sample_size, optim_interval=optim_interval, h2_panel_mode=mode, weights=weights,
+                            chisq_df=chisq_df if output_pvals else 0)
+    Lmat, H = res[0], res[1]
     out = SimpleNamespace(L=Lmat)
     if method == "alt-grid":
         out.h2_panel = H
     else:
         out.h2_null_list = H
     if output_pvals:
-        out.log10Pvals_mat = lod2log10p(Lmat, chisq_df)
+        out.log10Pvals_mat = res[2]  # fused on the device before the copy-back (blmm_opts.chisq_df)
         out.Chisq_df = chisq_df
     return out
 
@@ -372,7 +413,7 @@ def scan(y, g, K, covar=None, weights=None, prior_variance: float = 0.0, prior_s
         raise BlmmError(L.E_INVALID, "Assumption keyword is not supported. Please enter null or alt.")
     if y.shape[1] != 1:
         raise BlmmError(L.E_ONE_TRAIT, "Can only handle one trait.")
-    y, g, C0, K = _prep(y, g, covar, K, weights, addIntercept)
+    y, g, C0, K, weights = _prep(y, g, covar, K, weights, addIntercept, eng)
     n = y.shape[0]
     if not permutation_test:
         # scan_null, src/scan.jl:310-360
@@ -381,7 +422,8 @@ def scan(y, g, K, covar=None, weights=None, prior_variance: float = 0.0, prior_s
         else:
             U, lam = decomposition
         lod, s2, h2 = eng.scan_null_host(y, g, C0, U, lam, reml=reml, prior_variance=prior_variance,
-                                         prior_sample_size=prior_sample_size, optim_interval=optim_interval)
+                                         prior_sample_size=prior_sample_size, optim_interval=optim_interval,
+                                         weights=weights)
         return SimpleNamespace(sigma2_e=float(s2[0]), h2_null=float(h2[0]), lod=lod[:, 0].copy())
     if perm_idx is None:
         from .synth import make_perm_indices
@@ -391,24 +433,24 @@ def scan(y, g, K, covar=None, weights=None, prior_variance: float = 0.0, prior_s
     else:
         U, lam = decomposition
     r = eng.scan_perms_host(y, g, C0, U, lam, perm_idx, reml=reml, prior_variance=prior_variance,
-                            prior_sample_size=prior_sample_size, optim_interval=optim_interval)
+                            prior_sample_size=prior_sample_size, optim_interval=optim_interval, weights=weights)
     return r
 
 
-def get_thresholds(L_perms: np.ndarray, signif_level: Sequence[float]):
-    """src/analysis_helpers/single_trait_analysis.jl:13-23 (Julia `quantile` = type 7)."""
-    peaks = np.max(np.asarray(L_perms), axis=0)
-    probs = 1.0 - np.asarray(signif_level, dtype=np.float64)
-    return SimpleNamespace(probs=probs, thrs=np.quantile(peaks, probs))
+def get_thresholds(L_perms: np.ndarray, signif_level: Sequence[float], engine: Optional[Engine] = None):
+    """src/analysis_helpers/single_trait_analysis.jl:13-23 (Julia `quantile` = type 7).  Given the full
+    L_perms matrix as in the reference; the column maxima are taken here, the quantiles on the device."""
+    return thresholds_from_max(np.max(np.asarray(L_perms), axis=0), signif_level, engine=engine)
 
 
-def thresholds_from_max(max_lod: np.ndarray, signif_level: Sequence[float]):
-    """get_thresholds from the per-permutation maxima the fused kernel returns (no L_perms needed)."""
-    probs = 1.0 - np.asarray(signif_level, dtype=np.float64)
-    return SimpleNamespace(probs=probs, thrs=np.quantile(np.asarray(max_lod), probs))
+def thresholds_from_max(max_lod: np.ndarray, signif_level: Sequence[float], engine: Optional[Engine] = None):
+    """get_thresholds from the per-permutation maxima the fused kernel returns (no L_perms needed):
+    blmm_thresholds sorts them on the device and interpolates the type-7 quantiles."""
+    eng = engine or default_engine()
+    sl = np.asarray(signif_level, dtype=np.float64)
+    return SimpleNamespace(probs=1.0 - sl, thrs=eng.thresholds(max_lod, sl))
 
 
-def lod2log10p(lod, df: int = 1):
-    """src/util.jl:199-206 (host; the fused epilogue version is a later step)."""
-    from scipy.stats import chi2
-    return -chi2.logsf(np.asarray(lod) * 2.0 * np.log(10.0), df) / np.log(10.0)
+def lod2log10p(lod, df: int = 1, engine: Optional[Engine] = None):
+    """src/util.jl:199-206 on the device (blmm_lod2log10p)."""
+    return (engine or default_engine()).lod2log10p(lod, df)

@@ -21,7 +21,7 @@ using namespace blmm;
 enum Slot {
   S_Y_IN, S_G_IN, S_C_IN, S_U_IN, S_LAM, S_GRID, S_Y0, S_C0, S_G0, S_YR, S_W, S_SW, S_Q, S_SLW, S_LDS,
   S_ELL, S_RSS, S_BEST, S_ELLMAX, S_MOP, S_TOP, S_E, S_ET, S_BINS, S_TILEK0, S_COLMAP, S_L, S_H2P, S_H2V,
-  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_LOGTAB, S_XOP, S_DYINV,
+  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_LOGTAB, S_XOP, S_DYINV, S_PVAL, S_OBSW, S_UW, S_SORT, S_SORTTMP, S_PROBS,
   S_COUNT
 };
 
@@ -127,6 +127,13 @@ Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool
   R.p = with_markers ? pr->p : 0;
   const size_t n = (size_t)pr->n;
   const double* dU = stage_in(ctx, S_U_IN, pr->U, n * n, mem_space);
+  if (pr->obs_weights) {
+    // U'(w .* X) = (w .* U)'X: fold the observation weights into the rotation matrix once
+    const double* dw = stage_in(ctx, S_OBSW, pr->obs_weights, n, mem_space);
+    double* Uw = ws<double>(ctx, S_UW, n * n);
+    ctx->launches += launch_scale_rows(dU, dw, pr->n, pr->n, Uw, ctx->sm_count, ctx->stream);
+    dU = Uw;
+  }
   R.lambda = stage_in(ctx, S_LAM, pr->lambda, n, mem_space);
   const double* dC = stage_in(ctx, S_C_IN, pr->Covar, n * R.c, mem_space);
   R.C0 = ws<double>(ctx, S_C0, (size_t)R.n_pad * R.c);
@@ -173,6 +180,17 @@ void copy_out(blmm_ctx* ctx, double* dst, const double* src_dev, size_t count, i
   CUDA_TRY(cudaMemcpyAsync(dst, src_dev, count * sizeof(double),
                            mem_space == BLMM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                            ctx->stream));
+}
+
+// output_pvals: -log10 p of every LOD, computed on the device before anything is copied back
+double* pvals_after_scan(blmm_ctx* ctx, const blmm_opts* o, const double* dL, int64_t p, int64_t m, int64_t ldL) {
+  if (o->chisq_df <= 0) return nullptr;
+  if (o->chisq_df > 1000) throw Fail{BLMM_E_INVALID, "chisq_df must be in 1..1000"};
+  if (!o->log10p_out) throw Fail{BLMM_E_INVALID, "chisq_df > 0 but log10p_out is NULL"};
+  const bool dev = o->mem_space == BLMM_MEM_DEVICE;
+  double* dP = dev ? o->log10p_out : ws<double>(ctx, S_PVAL, (size_t)p * m);
+  ctx->launches += launch_lod2log10p(dL, p, m, ldL, ldL, o->chisq_df, dP, ctx->sm_count, ctx->stream);
+  return dP;
 }
 
 void run_scan(blmm_ctx* ctx, ScanParams P) {
@@ -287,7 +305,7 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     P.n_tiles_t = (int)(tcol_pad / SCAN_TT);
     P.nk = 1;
   }
-  if (ms == BLMM_MEM_HOST && alt && P.n_tiles_t >= 16) {
+  if (ms == BLMM_MEM_HOST && alt && P.n_tiles_t >= 16 && o->chisq_df <= 0) {
     // Host-buffer alt-grid: the p x m panels (2 x 2 GB at BXD size) leave over PCIe, which takes ~5x
     // the scan itself.  Scan the trait tiles in chunks and copy each chunk's columns back on a
     // second stream while the next chunk is scanned.
@@ -318,10 +336,14 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     return BLMM_OK;
   }
   run_scan(ctx, P);
+  double* dP = pvals_after_scan(ctx, o, dL, p, m, P.ldL);
 
   if (ms == BLMM_MEM_HOST) {
     CUDA_TRY(cudaMemcpy2DAsync(L_out, ld * sizeof(double), dL, p * sizeof(double), p * sizeof(double), m,
                                cudaMemcpyDeviceToHost, ctx->stream));
+    if (dP)
+      CUDA_TRY(cudaMemcpy2DAsync(o->log10p_out, ld * sizeof(double), dP, p * sizeof(double), p * sizeof(double), m,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
     if (dH)
       CUDA_TRY(cudaMemcpy2DAsync(h2_out, ld * sizeof(double), dH, p * sizeof(double), p * sizeof(double), m,
                                  cudaMemcpyDeviceToHost, ctx->stream));
@@ -458,9 +480,13 @@ int bulkscan_exact(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, do
     ctx->scan_timed = true;
   }
   CUDA_TRY(cudaGetLastError());
+  double* dP = pvals_after_scan(ctx, o, dL, p, m, P.ldL);
   if (!dev) {
     CUDA_TRY(cudaMemcpy2DAsync(L_out, ld * sizeof(double), dL, p * sizeof(double), p * sizeof(double), m,
                                cudaMemcpyDeviceToHost, ctx->stream));
+    if (dP)
+      CUDA_TRY(cudaMemcpy2DAsync(o->log10p_out, ld * sizeof(double), dP, p * sizeof(double), p * sizeof(double), m,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
     copy_out(ctx, h2_out, h2, m, ms);
     copy_out(ctx, sigma2_out, s2, m, ms);
     finish_and_check(ctx);
@@ -661,6 +687,64 @@ int rotate(blmm_ctx* ctx, const blmm_problem* pr, double* Y0_out, double* X0_out
   return BLMM_OK;
 }
 
+int lod2log10p(blmm_ctx* ctx, const double* lod, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, int df,
+               double* out, int ms) {
+  if (rows < 0 || cols < 0 || (rows * cols > 0 && (!lod || !out))) throw Fail{BLMM_E_INVALID, "bad lod2log10p arguments"};
+  if (df < 1 || df > 1000) throw Fail{BLMM_E_INVALID, "chisq_df must be in 1..1000"};
+  if (rows * cols == 0) return BLMM_OK;
+  if (!ld_in) ld_in = rows;
+  if (!ld_out) ld_out = rows;
+  if (ld_in < rows || ld_out < rows) throw Fail{BLMM_E_INVALID, "leading dimension < rows"};
+  if (ms == BLMM_MEM_DEVICE) {
+    ctx->launches += launch_lod2log10p(lod, rows, cols, ld_in, ld_out, df, out, ctx->sm_count, ctx->stream);
+    CUDA_TRY(cudaGetLastError());
+    return BLMM_OK;
+  }
+  double* d = ws<double>(ctx, S_PVAL, (size_t)rows * cols);
+  CUDA_TRY(cudaMemcpy2DAsync(d, rows * sizeof(double), lod, ld_in * sizeof(double), rows * sizeof(double), cols,
+                             cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_lod2log10p(d, rows, cols, rows, rows, df, d, ctx->sm_count, ctx->stream);
+  CUDA_TRY(cudaMemcpy2DAsync(out, ld_out * sizeof(double), d, rows * sizeof(double), rows * sizeof(double), cols,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(cudaGetLastError());
+  return BLMM_OK;
+}
+
+int thresholds(blmm_ctx* ctx, const double* maxlod, int64_t nperms, const double* signif, int nlev, double* thrs,
+               int ms) {
+  if (nperms < 1 || !maxlod || nlev < 0 || (nlev > 0 && (!signif || !thrs)))
+    throw Fail{BLMM_E_INVALID, "bad thresholds arguments"};
+  if (nlev == 0) return BLMM_OK;
+  const double* dmax = stage_in(ctx, S_COLMAX, maxlod, nperms, ms);
+  std::vector<double> probs(nlev);
+  for (int i = 0; i < nlev; ++i) probs[i] = 1.0 - signif[i];
+  double* d_probs = ws<double>(ctx, S_PROBS, 2 * (size_t)nlev);
+  CUDA_TRY(cudaMemcpyAsync(d_probs, probs.data(), nlev * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  double* sorted = ws<double>(ctx, S_SORT, nperms);
+  const size_t tmp_bytes = thresholds_workspace_bytes(nperms);
+  void* tmp = ws<unsigned char>(ctx, S_SORTTMP, tmp_bytes);
+  ctx->launches += launch_thresholds(dmax, nperms, d_probs, nlev, sorted, tmp, tmp_bytes, d_probs + nlev, ctx->stream);
+  CUDA_TRY(cudaMemcpyAsync(thrs, d_probs + nlev, nlev * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // `probs` is a host temporary; thrs is a host array
+  CUDA_TRY(cudaGetLastError());
+  return BLMM_OK;
+}
+
+int weight_kinship(blmm_ctx* ctx, int64_t n, const double* K, const double* w, double* K_out, int ms) {
+  if (n <= 0 || !K || !w || !K_out) throw Fail{BLMM_E_INVALID, "bad weight_kinship arguments"};
+  const double* dK = stage_in(ctx, S_KIN, K, (size_t)n * n, ms);
+  const double* dw = stage_in(ctx, S_OBSW, w, n, ms);
+  double* out = (ms == BLMM_MEM_DEVICE) ? K_out : ws<double>(ctx, S_EIGV, (size_t)n * n + n + 8);
+  ctx->launches += launch_weight_kinship(dK, dw, (int)n, out, ctx->stream);
+  CUDA_TRY(cudaGetLastError());
+  if (ms == BLMM_MEM_HOST) {
+    copy_out(ctx, K_out, out, (size_t)n * n, ms);
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  return BLMM_OK;
+}
+
 template <typename F>
 int guarded(blmm_ctx* ctx, F&& f) {
   if (!ctx) return BLMM_E_INVALID;
@@ -827,6 +911,20 @@ int blmm_scan_null(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opt
     if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
     return bulkscan_exact(ctx, prob, opts, lod_out, h2_out, sigma2_out);
   });
+}
+
+int blmm_lod2log10p(blmm_ctx* ctx, const double* lod, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, int df,
+                    double* out, int mem_space) {
+  return guarded(ctx, [&] { return lod2log10p(ctx, lod, rows, cols, ld_in, ld_out, df, out, mem_space); });
+}
+
+int blmm_thresholds(blmm_ctx* ctx, const double* maxlod, int64_t nperms, const double* signif_level, int nlev,
+                    double* thrs_out, int mem_space) {
+  return guarded(ctx, [&] { return thresholds(ctx, maxlod, nperms, signif_level, nlev, thrs_out, mem_space); });
+}
+
+int blmm_weight_kinship(blmm_ctx* ctx, int64_t n, const double* K, const double* w, double* K_out, int mem_space) {
+  return guarded(ctx, [&] { return weight_kinship(ctx, n, K, w, K_out, mem_space); });
 }
 
 }  // extern "C"

@@ -184,4 +184,15 @@ int launch_exact_columns(const double* Yr, const double* h2, const double* lambd
 int launch_scan_exact(const StreamParams& P, int c, int sm_count, cudaStream_t stream);
 int launch_scan_stream_grid(const StreamParams& P, int sm_count, cudaStream_t stream);
 
+// ---- post-processing (blmm_post.cu) -------------------------------------------------------------
+int launch_lod2log10p(const double* lod, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, int df,
+                      double* out, int sm_count, cudaStream_t stream);
+size_t thresholds_workspace_bytes(int64_t n);
+int launch_thresholds(const double* maxlod, int64_t n, const double* probs_dev, int nprob, double* sorted,
+                      void* tmp, size_t tmp_bytes, double* out, cudaStream_t stream);
+// out = diag(w) * X (X: n x cols column-major, ld n); out may alias X
+int launch_scale_rows(const double* X, const double* w, int64_t n, int64_t cols, double* out, int sm_count,
+                      cudaStream_t stream);
+int launch_weight_kinship(const double* K, const double* w, int n, double* out, cudaStream_t stream);
+
 }  // namespace blmm

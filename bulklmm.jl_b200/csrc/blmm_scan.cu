@@ -1,16 +1,24 @@
 // The fused marker x trait scan kernel (see ScanParams in blmm_kernels.cuh for the arithmetic).
 //
-// Structure (sm_100a): persistent CTAs, one per SM, 8 warps (2 per SM sub-partition, so every
-// thread may hold up to 255 registers: accumulators + running minima + counters + double-buffered
-// fragments stay in registers).  A CTA owns a contiguous range of (trait tile, marker tile) units.
-// The trait tile (128 traits x whole K) stays resident in shared memory; for every unit the
-// k-list's marker tiles (64 markers x whole K, plus that k's per-trait scalars e/et) stream
-// through a 2-3 stage ring filled with 1-D bulk asynchronous copies (cp.async.bulk -> UBLKCP, the
-// TMA engine; mbarrier transaction counts), issued by one elected thread NS-1 iterations ahead.
-// Each warp owns a 32 marker x 32 trait block: FP64 tensor-core mma.sync m8n8k4 (DMMA.8x8x4)
-// over the K-chunked operands, then the per-k epilogue in registers (v = e - d^2*et, running
-// min, tmax! counter), and ONE logarithm per output after the last k.  LOD / h2 panels are
-// written once with streaming stores; nothing per-grid-point touches HBM.
+// Structure (sm_100a): persistent CTAs, one per SM, 16 warps (4 per SM sub-partition, <= 128
+// registers per thread).  A CTA owns a contiguous range of (trait tile, marker tile) units.  The trait
+// tile (128 traits x whole K) stays resident in shared memory; for every unit the k-list's marker
+// tiles (64 markers x whole K, plus that k's per-trait scalars e/et) stream through a 2-3 stage ring
+// filled with 1-D bulk asynchronous copies (cp.async.bulk -> UBLKCP, the TMA engine; mbarrier
+// transaction counts); the last warp to release a stage refills it.
+// Each warp owns a 32 marker x 16 trait block: FP64 tensor-core mma.sync m8n8k4 (DMMA.8x8x4) over the
+// K-chunked operands, then the per-k epilogue in registers (v = e - d^2*et, running min, tmax!
+// counter), and ONE logarithm per output after the last k.  LOD / h2 panels are written once with
+// streaming stores; nothing per-grid-point touches HBM.
+//
+// Ping-pong ordering.  On B200 DMMA and scalar FP64 share one pipe that a single warp per
+// sub-partition can saturate, so what costs time is every warp of a sub-partition leaving the DMMA
+// loop together (they consume the same stage and are served round-robin, so they run in lock step)
+// and the pipe idling through the epilogues.  The warps are therefore split into two groups
+// (marker rows 0-31 / 32-63 of the tile) that take turns in the DMMA loop, per sub-partition, through
+// a pair of named barriers: while one group multiplies, the other runs its epilogue (running-min
+// update, logarithm, stores) and the scalar FP64 work fills DMMA issue gaps instead of serialising
+// with it.
 #include <math.h>
 
 #include "blmm_kernels.cuh"
@@ -21,11 +29,15 @@ namespace {
 
 constexpr int TT = SCAN_TT;  // traits per CTA tile
 constexpr int MT = SCAN_MT;  // markers per CTA tile
+constexpr int BT = 2;        // 8-trait atoms per warp: 16 warps of 32 markers x 16 traits
+constexpr int WT_WARPS = TT / (8 * BT);
+constexpr int NWARPS = 2 * WT_WARPS;
+constexpr int NTHREADS = 32 * NWARPS;
 constexpr int SMEM_LIMIT = 227 * 1024;
-#ifndef BLMM_SCAN_BT
-#define BLMM_SCAN_BT 2
-#endif
 constexpr int GRID_MAX = 256;
+constexpr int LTAB = 512;  // entries of the in-kernel logarithm table
+
+static_assert(NWARPS == 16 && NTHREADS == 512, "ping-pong barrier counts assume 16 warps");
 
 struct SmemPlan {
   int nstage;
@@ -34,7 +46,7 @@ struct SmemPlan {
   size_t bytes;
 };
 
-constexpr size_t FIXED_SMEM = (size_t)LOGTAB_N * 16 + GRID_MAX * 8 + 128;
+constexpr size_t FIXED_SMEM = (size_t)LTAB * 16 + GRID_MAX * 8 + 2 * TT * 4 + 128;
 
 __host__ __device__ inline SmemPlan plan_smem(int nq) {
   SmemPlan s;
@@ -56,20 +68,61 @@ __device__ __forceinline__ void dmma884_zero(double& c0, double& c1, double a, d
       : "d"(a), "d"(b), "d"(0.0));
 }
 
-// BT = 8-trait atoms per warp: BT = 4 -> 8 warps of 32 markers x 32 traits, BT = 2 -> 16 warps of
-// 32 markers x 16 traits (4 warps per SM sub-partition, <= 128 registers per thread).
-template <int NQ, bool ARGMAX, int BT, bool HAS_E>
-__global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const ScanParams P) {
-  constexpr int WT_WARPS = TT / (8 * BT);  // warps along the trait dimension
-  constexpr int NWARPS = 2 * WT_WARPS;
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// LOD = -(n/2) log10(v) for the final epilogue, ~8 FP64 operations (the FP64 pipe is shared with DMMA).
+// v = 2^e * m, m in [0.75, 1.5); the table gives rcp ~ 1/c and (n/2) log10(rcp) for m's interval
+// (256 intervals over [0.75, 1), 256 over [1, 1.5)); r = m*rcp - 1, |r| < 2^-9; log1p(r) by a 5-term
+// series.  The two intervals touching 1 use rcp = 1 exactly, so LODs keep full relative accuracy as
+// v -> 1 (LOD -> 0): relative error <= r^5/6 ~ 1e-16 there, absolute error ~1e-19 * n elsewhere.
+// `special` is raised for operands outside the positive normal range (fixed up by the caller).
+__device__ __forceinline__ double fast_lod(double v, const double2* __restrict__ tab, double c_ln, double c_e,
+                                           bool& special) {
+  const int hi = __double2hiint(v), lo = __double2loint(v);
+  const int ix = hi - 0x3fe80000;
+  const int e = ix >> 20;
+  const double m = __hiloint2double(hi - (e << 20), lo);
+  const double2 t = tab[(ix >> 11) & (LTAB - 1)];
+  const double r = fma(m, t.x, -1.0);
+  double q = fma(r, 1.0 / 5.0, -1.0 / 4.0);
+  q = fma(q, r, 1.0 / 3.0);
+  q = fma(q, r, -1.0 / 2.0);
+  q = fma(q, r, 1.0);
+  const double lp = q * r;
+  special |= (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
+  // c_ln = -(n/2) log10(e), c_e = -(n/2) log10(2), t.y = -(n/2) * (-log10 rcp)
+  return fma(lp, c_ln, fma((double)e, c_e, t.y));
+}
+
+// IEEE results for the operands fast_lod flags: v = 0 (r^2 = 1) -> LOD = +inf (a subnormal v,
+// unreachable as 1 - r^2, is treated as 0); v < 0 -> NaN (Julia's log10 throws there); v = +inf ->
+// -inf; NaN passes through.
+__device__ __forceinline__ double fix_lod(double v, double res) {
+  const int hi = __double2hiint(v);
+  res = ((unsigned)hi < 0x00100000u) ? INFINITY : res;
+  res = (hi < 0) ? __longlong_as_double(0x7ff8000000000000LL) : res;
+  res = (hi >= 0x7ff00000) ? -v : res;
+  return res;
+}
+
+// HAS_E = false: one-element k-lists with e = 1 (null-grid bins, permutations) — no running minimum,
+// no counter, no h2 panel.  COLMAX: also reduce the per-column maximum (permutation thresholds).
+template <int NQ, bool ARGMAX, bool HAS_E, bool COLMAX>
+__global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SmemPlan plan = plan_smem(NQ);
   const int NS = plan.nstage;
   double* top = reinterpret_cast<double*>(smem_raw);
   double* stages = top + plan.top_doubles;
   double2* logtab = reinterpret_cast<double2*>(stages + NS * plan.stage_doubles);
-  double* grid_s = reinterpret_cast<double*>(logtab + LOGTAB_N);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(grid_s + GRID_MAX);
+  double* grid_s = reinterpret_cast<double*>(logtab + LTAB);
+  int* colmap_s = reinterpret_cast<int*>(grid_s + GRID_MAX);  // [2][TT], by trait-tile parity
+  uint64_t* bars = reinterpret_cast<uint64_t*>(colmap_s + 2 * TT);
   uint64_t* full = bars;  // [NS]
   uint64_t* top_full = bars + 3;
   uint64_t* top_empty = bars + 4;
@@ -89,16 +142,30 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
     mbar_init(top_empty, NWARPS);
     mbar_fence_init();
   }
-  if (tid < LOGTAB_N) logtab[tid] = reinterpret_cast<const double2*>(P.logtab)[tid];
+  {
+    // logarithm table, scaled by -(n/2) so that the epilogue produces the LOD directly
+    const int i = tid;
+    double c;
+    if (i == LTAB / 2 - 1 || i == LTAB / 2)
+      c = 1.0;
+    else if (i < LTAB / 2)
+      c = 0.75 + ((double)i + 0.5) * (0.25 / (LTAB / 2));
+    else
+      c = 1.0 + ((double)(i - LTAB / 2) + 0.5) * (0.5 / (LTAB / 2));
+    const double rcp = 1.0 / c;
+    logtab[i] = make_double2(rcp, (rcp == 1.0) ? 0.0 : P.half_n * log10(rcp));
+  }
   if (P.grid && tid < P.ngrid) grid_s[tid] = P.grid[tid];
   __syncthreads();
+  const double c_ln = -P.half_n * 0.43429448190325182765;
+  const double c_e = -P.half_n * 0.30102999566398119521;
 
   const int n_tiles = P.n_tiles_dev ? *P.n_tiles_dev : P.n_tiles_t;
   const int n_mt = P.p_pad / MT;
   const int64_t units = (int64_t)n_tiles * n_mt;  // < 2^31 (checked by the launcher)
   const int u0 = (int)(units * blockIdx.x / gridDim.x);
   const int u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
-  const int nk = P.nk;
+  const int nk = HAS_E ? P.nk : 1;
   const int total_it = (u1 - u0) * nk;
   constexpr uint32_t marker_chunk_bytes = MT * KC * 8;
   constexpr uint32_t trait_chunk_bytes = TT * KC * 8;
@@ -140,10 +207,16 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
   }
 
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp / WT_WARPS;  // marker sub-block (0..1)
+  const int wm = warp / WT_WARPS;  // marker sub-block (0..1) = ping-pong group
   const int wt = warp % WT_WARPS;  // trait sub-block
   const int aoff = (wm * 32 + g) * KC + t;
   const int boff = (wt * (8 * BT) + g) * KC + t;
+  // Ping-pong: the two groups alternate in the DMMA loop, independently on every SM sub-partition
+  // (warps w, w+4 of a group share sub-partition w & 3).  Barrier 1 + 2*(w&3) + grp is "group grp may
+  // multiply"; 128 = the four warps of the sub-partition (two wait, two arrive).
+  const int my_turn = 1 + 2 * (warp & 3) + wm;
+  const int their_turn = 1 + 2 * (warp & 3) + (wm ^ 1);
+  if (wm == 1) named_bar_arrive(their_turn, 128);
 
   int it = 0, s = 0;
   uint32_t sphase = 0;  // parity of the ring round
@@ -152,11 +225,14 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
     if (tt != cur_tt) {
       if (tid == 0) {
         if (ntop > 0) mbar_wait(top_empty, (ntop - 1) & 1);
-        mbar_arrive_expect_tx(top_full, (uint32_t)NQ * trait_chunk_bytes);
+        mbar_arrive_expect_tx(top_full, (uint32_t)NQ * trait_chunk_bytes + (P.col_map ? TT * 4 : 0));
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
           bulk_g2s(top + (size_t)q * TT * KC, P.Top + ((size_t)q * P.tcol_pad + (size_t)tt * TT) * KC,
                    trait_chunk_bytes, top_full);
+        // The packed-column -> output-column map of the tile is read by the final epilogue, which can
+        // still be running for the previous tile in other warps: two copies, by tile parity.
+        if (P.col_map) bulk_g2s(colmap_s + (ntop & 1) * TT, P.col_map + (size_t)tt * TT, TT * 4, top_full);
       }
       mbar_wait(top_full, ntop & 1);
       ++ntop;
@@ -165,14 +241,17 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
     const bool last_of_tt = (u + 1 == u1) || (mt + 1 == n_mt);
 
     double acc[4][BT][2];
-    double vmin[4][BT][2];
-    uint32_t cnt[2 * BT];
+    double vmin[HAS_E ? 4 : 1][BT][2];
+    uint32_t cnt[HAS_E ? 2 * BT : 1];
+    if (HAS_E) {
 #pragma unroll
-    for (int i = 0; i < 2 * BT; ++i) cnt[i] = 0u;
+      for (int i = 0; i < 2 * BT; ++i) cnt[i] = 0u;
+    }
 
     for (int kk = 0; kk < nk; ++kk, ++it) {
       mbar_wait(&full[s], sphase);
       const double* ms = stages + (size_t)s * plan.stage_doubles;
+      named_bar_sync(my_turn, 128);
       {
         // K loop, fully unrolled, fragments double-buffered in registers
         const double* ap = ms + aoff;
@@ -203,6 +282,7 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
             }
         }
       }
+      named_bar_arrive(their_turn, 128);
       // per-k trait scalars for this lane's 2*BT trait columns
       double ek[BT][2], etk[BT][2];
       {
@@ -239,29 +319,41 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
         sphase ^= 1u;
       }
 
-      const bool first = (kk == 0);
+      if (HAS_E) {
+        const bool first = (kk == 0);
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < BT; ++b)
+          for (int b = 0; b < BT; ++b)
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const double d = acc[a][b][cc];
-            const double v = fma(-(d * d), etk[b][cc], ek[b][cc]);
-            // strict `<` as `max .< to_compare` in tmax!, on the bit patterns (integer pipe; the
-            // FP64 pipe is the bottleneck).  Equivalent for the non-negative v that occur; a
-            // negative v (r^2 > 1 by rounding) orders below every positive one, as it should.
-            const bool better = __double_as_longlong(v) < __double_as_longlong(vmin[a][b][cc]);
-            const bool upd = first || better;
-            vmin[a][b][cc] = upd ? v : vmin[a][b][cc];
-            const int o = (a * BT + b) * 2 + cc;
-            const int sh = (o & 3) * 8;
-            if (ARGMAX) {
-              if (upd) cnt[o >> 2] = (cnt[o >> 2] & ~(0xFFu << sh)) | ((uint32_t)kk << sh);
-            } else {
-              if (better && !first) cnt[o >> 2] += (1u << sh);
+            for (int cc = 0; cc < 2; ++cc) {
+              const double d = acc[a][b][cc];
+              const double v = fma(-(d * d), etk[b][cc], ek[b][cc]);
+              // strict `<` as `max .< to_compare` in tmax!, on the bit patterns (integer pipe; the
+              // FP64 pipe is the bottleneck).  Equivalent for the non-negative v that occur; a
+              // negative v (r^2 > 1 by rounding) orders below every positive one, as it should.
+              const bool better = __double_as_longlong(v) < __double_as_longlong(vmin[a][b][cc]);
+              const bool upd = first || better;
+              vmin[a][b][cc] = upd ? v : vmin[a][b][cc];
+              const int o = (a * BT + b) * 2 + cc;
+              const int sh = (o & 3) * 8;
+              if (ARGMAX) {
+                if (upd) cnt[o >> 2] = (cnt[o >> 2] & ~(0xFFu << sh)) | ((uint32_t)kk << sh);
+              } else {
+                if (better && !first) cnt[o >> 2] += (1u << sh);
+              }
             }
-          }
+      } else {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < BT; ++b)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const double d = acc[a][b][cc];
+              acc[a][b][cc] = fma(-(d * d), etk[b][cc], 1.0);
+            }
+      }
     }
 
     // final epilogue: one logarithm per output, streaming stores
@@ -272,24 +364,28 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
 #pragma unroll
       for (int b = 0; b < BT; ++b)
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) lod[a][b][cc] = fast_log10(vmin[a][b][cc], logtab, special);
+        for (int cc = 0; cc < 2; ++cc)
+          lod[a][b][cc] = fast_lod(HAS_E ? vmin[a][b][cc] : acc[a][b][cc], logtab, c_ln, c_e, special);
     if (__any_sync(0xffffffffu, special)) {
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < BT; ++b)
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) lod[a][b][cc] = fix_log10(vmin[a][b][cc], lod[a][b][cc]);
+          for (int cc = 0; cc < 2; ++cc)
+            lod[a][b][cc] = fix_lod(HAS_E ? vmin[a][b][cc] : acc[a][b][cc], lod[a][b][cc]);
     }
-    const int k0 = P.tile_k0 ? P.tile_k0[tt] : 0;
-    const int kbase = ARGMAX ? k0 : 0;
-    const int i_base = mt * MT + wm * 32 + g;
+    const int kbase = (HAS_E && ARGMAX && P.tile_k0) ? P.tile_k0[tt] : 0;
+    const int row0 = mt * MT + wm * 32 + g;
+    const bool full_rows = (mt + 1) * MT <= P.p;  // every marker row of the tile exists
+    const int* cmap = colmap_s + ((ntop - 1) & 1) * TT;
 #pragma unroll
     for (int b = 0; b < BT; ++b)
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
-        const int64_t pos = (int64_t)tt * TT + wt * (8 * BT) + b * 8 + 2 * t + cc;
-        const int64_t col = P.col_map ? (int64_t)P.col_map[pos] : (pos < P.m ? pos : -1);
+        const int posl = wt * (8 * BT) + b * 8 + 2 * t + cc;
+        const int64_t pos = (int64_t)tt * TT + posl;
+        const int64_t col = P.col_map ? (int64_t)cmap[posl] : (pos < P.m ? pos : -1);
         // output column pointers (column 0 may be split off, see ScanParams::L0)
         double* Lc = nullptr;
         double* Hc = nullptr;
@@ -297,33 +393,48 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
         if (col >= 0) {
           if (P.L0) {
             if (col == 0) {
-              Lc = P.L0;
+              Lc = P.L0 + row0;
             } else {
-              if (P.L) Lc = P.L + (col - 1) * P.ldL;
-              if (P.colmax) Mc = P.colmax + (col - 1);
+              if (P.L) Lc = P.L + (col - 1) * P.ldL + row0;
+              if (COLMAX) Mc = P.colmax + (col - 1);
             }
           } else {
-            if (P.L) Lc = P.L + col * P.ldL;
-            if (P.colmax) Mc = P.colmax + col;
+            if (P.L) Lc = P.L + col * P.ldL + row0;
+            if (COLMAX) Mc = P.colmax + col;
           }
-          if (P.H2) Hc = P.H2 + col * P.ldL;
+          if (HAS_E && P.H2) Hc = P.H2 + col * P.ldL + row0;
         }
-        double cmax = 0.0;
+        if (full_rows) {
+          if (Lc) {
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int i = i_base + a * 8;
-          const double l = -P.half_n * lod[a][b][cc];
-          if (i < P.p) {
-            if (Lc) st_stream(Lc + i, l);
-            if (Hc) {
+            for (int a = 0; a < 4; ++a) st_stream(Lc + a * 8, lod[a][b][cc]);
+          }
+          if (HAS_E && Hc) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
               const int o = (a * BT + b) * 2 + cc;
               const int cv = (int)((cnt[o >> 2] >> ((o & 3) * 8)) & 0xFFu);
-              st_stream(Hc + i, grid_s[kbase + cv]);
+              st_stream(Hc + a * 8, grid_s[kbase + cv]);
             }
-            cmax = fmax(cmax, l);
+          }
+        } else {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            if (row0 + a * 8 < P.p) {
+              if (Lc) st_stream(Lc + a * 8, lod[a][b][cc]);
+              if (HAS_E && Hc) {
+                const int o = (a * BT + b) * 2 + cc;
+                const int cv = (int)((cnt[o >> 2] >> ((o & 3) * 8)) & 0xFFu);
+                st_stream(Hc + a * 8, grid_s[kbase + cv]);
+              }
+            } else {
+              lod[a][b][cc] = 0.0;  // padded marker rows stay out of the column maximum
+            }
           }
         }
-        if (P.colmax) {
+        if (COLMAX) {
+          double cmax = fmax(fmax(lod[0][b][cc], lod[1][b][cc]), fmax(lod[2][b][cc], lod[3][b][cc]));
+          cmax = fmax(cmax, 0.0);
           cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, 4));
           cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, 8));
           cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, 16));
@@ -335,6 +446,8 @@ __global__ void __launch_bounds__(32 * 2 * (TT / (8 * BT)), 1) scan_kernel(const
       ++tt;
     }
   }
+  // consume the other group's last "your turn" so that no barrier is left half-complete at exit
+  if (wm == 0) named_bar_sync(my_turn, 128);
 }
 
 __global__ void logtab_kernel(double* tab) {
@@ -352,30 +465,32 @@ __global__ void logtab_kernel(double* tab) {
   tab[2 * i + 1] = (rcp == 1.0) ? 0.0 : -log10(rcp);
 }
 
-constexpr int SCAN_BT = BLMM_SCAN_BT;
-
-template <int NQ, bool ARGMAX, bool HAS_E>
+template <int NQ, bool ARGMAX, bool HAS_E, bool COLMAX>
 void launch_one(const ScanParams& P, int sm_count, cudaStream_t stream) {
   const SmemPlan plan = plan_smem(NQ);
-  constexpr int threads = 32 * 2 * (TT / (8 * SCAN_BT));
-  cudaFuncSetAttribute(scan_kernel<NQ, ARGMAX, SCAN_BT, HAS_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  scan_kernel<NQ, ARGMAX, SCAN_BT, HAS_E><<<sm_count, threads, plan.bytes, stream>>>(P);
+  cudaFuncSetAttribute(scan_kernel<NQ, ARGMAX, HAS_E, COLMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  scan_kernel<NQ, ARGMAX, HAS_E, COLMAX><<<sm_count, NTHREADS, plan.bytes, stream>>>(P);
 }
 
 template <int NQ>
 void launch_nq(const ScanParams& P, int sm_count, cudaStream_t stream) {
   if (P.e) {
     if (P.argmax_mode)
-      launch_one<NQ, true, true>(P, sm_count, stream);
+      launch_one<NQ, true, true, false>(P, sm_count, stream);
     else
-      launch_one<NQ, false, true>(P, sm_count, stream);
+      launch_one<NQ, false, true, false>(P, sm_count, stream);
   } else {
     // one-element k-lists (null-grid bins, permutations): the h2 panel is not produced
-    launch_one<NQ, false, false>(P, sm_count, stream);
+    if (P.colmax)
+      launch_one<NQ, false, false, true>(P, sm_count, stream);
+    else
+      launch_one<NQ, false, false, false>(P, sm_count, stream);
   }
 }
 
 }  // namespace
+
+int launch_scan_v3(const ScanParams& P, int sm_count, cudaStream_t stream);  // blmm_scan_v3.cu (A/B only)
 
 int scan_max_nq(int nk) {
   (void)nk;
@@ -390,6 +505,12 @@ int launch_logtab(double* tab, cudaStream_t stream) {
 }
 
 int launch_scan(const ScanParams& P, int sm_count, cudaStream_t stream) {
+  static const bool use_v3 = [] {
+    const char* v = getenv("BLMM_SCAN_KERNEL");
+    return v && v[0] == 'v' && v[1] == '3';
+  }();
+  if (use_v3) return launch_scan_v3(P, sm_count, stream);
+  if ((!P.e && P.nk != 1) || (P.e && P.colmax)) return 0;  // combinations the kernel variants do not cover
   switch (P.nq) {
     case 1: launch_nq<1>(P, sm_count, stream); break;
     case 2: launch_nq<2>(P, sm_count, stream); break;

@@ -18,7 +18,7 @@ module BulkLMMB200
 using LinearAlgebra, Random, Statistics
 
 export bulkscan, bulkscan_null, bulkscan_null_grid, bulkscan_alt_grid, scan, calcKinship, transform_rotation,
-       get_thresholds
+       get_thresholds, thresholds_from_max, lod2log10p
 
 const libblmm = get(ENV, "BLMM_B200_LIB", "libblmm_b200.so")
 
@@ -31,6 +31,7 @@ const DECOMP_EIGEN, DECOMP_SVD = Cint(0), Cint(1)
 struct BlmmProblem            # blmm_problem
     n::Int64; p::Int64; m::Int64; c::Int64
     Y::Ptr{Float64}; G::Ptr{Float64}; Covar::Ptr{Float64}; U::Ptr{Float64}; lambda::Ptr{Float64}
+    obs_weights::Ptr{Float64}   # C_NULL or the `weights` keyword (rows scaled on the device)
 end
 
 struct BlmmOpts               # blmm_opts
@@ -39,7 +40,11 @@ struct BlmmOpts               # blmm_opts
     h2_grid::Ptr{Float64}; ngrid::Int32
     optim_interval::Int32; h2_panel_mode::Int32; mem_space::Int32
     ld_out::Int64
+    chisq_df::Int32; reserved::Int32
+    log10p_out::Ptr{Float64}    # `output_pvals`: -log10 p of every LOD, written next to L
 end
+BlmmOpts(method, reml, pv, pss, grid, ngrid, oi, mode, ms, ld) =
+    BlmmOpts(method, reml, pv, pss, grid, ngrid, oi, mode, ms, ld, Int32(0), Int32(0), Ptr{Float64}(C_NULL))
 
 mutable struct Context
     handle::Ptr{Cvoid}
@@ -95,65 +100,82 @@ function transform_rotation(y::Array{Float64, 2}, g::Array{Float64, 2}, K::Array
     X = addIntercept ? [ones(n, 1) g] : g
     U, lambda = decompose(K; decomp_scheme = decomp_scheme, ctx = ctx)
     Y0 = similar(y); X0 = similar(X)
-    prob = BlmmProblem(n, 0, size(y, 2), size(X, 2), pointer(y), C_NULL, pointer(X), pointer(U), pointer(lambda))
+    prob = BlmmProblem(n, 0, size(y, 2), size(X, 2), pointer(y), C_NULL, pointer(X), pointer(U), pointer(lambda), C_NULL)
     GC.@preserve y X U lambda Y0 X0 check(ctx, ccall((:blmm_rotate, libblmm), Cint,
         (Ptr{Cvoid}, Ref{BlmmProblem}, Ptr{Float64}, Ptr{Float64}, Cint), ctx.handle, prob, Y0, X0, BLMM_MEM_HOST))
     return Y0, X0, lambda
 end
 
-# Argument plumbing shared by the bulkscan methods: intercept column and the observation-weight
-# pre-scaling block of src/bulkscan.jl:231-250, 351-370, 457-476.
-function prep(Y, G, Covar, K, weights, addIntercept)
+# Argument plumbing shared by the scan entry points: the intercept column.  The observation weights
+# (src/bulkscan.jl:231-250, 351-370, 457-476; src/scan.jl:204-222) cross the ABI as
+# blmm_problem.obs_weights — Y, G and Covar are row-scaled on the device — and only the n x n kinship
+# becomes W*K*W up front (blmm_weight_kinship) because it feeds the decomposition.
+function prep(Y, G, Covar, K, weights, addIntercept; ctx::Context = default_context())
     n = size(Y, 1)
     if (size(G, 1) != n) | (size(K, 1) != n)
         throw(error("Dimension mismatch."))
     end
     C = addIntercept ? [ones(n, 1) Covar] : Covar
+    K = Array{Float64, 2}(K)
+    w = Float64[]
     if !ismissing(weights)
-        Y = weights .* Y; G = weights .* G; C = weights .* C
-        K = weights .* K .* weights'
+        length(weights) == n || throw(error("Dimension mismatch."))
+        w = Array{Float64, 1}(weights)
+        Kw = similar(K)
+        GC.@preserve K w Kw check(ctx, ccall((:blmm_weight_kinship, libblmm), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint), ctx.handle, n, K, w, Kw, BLMM_MEM_HOST))
+        K = Kw
     end
-    return Array{Float64, 2}(Y), Array{Float64, 2}(G), Array{Float64, 2}(C), Array{Float64, 2}(K)
+    return Array{Float64, 2}(Y), Array{Float64, 2}(G), Array{Float64, 2}(C), K, w
 end
+wptr(w::Array{Float64, 1}) = isempty(w) ? Ptr{Float64}(C_NULL) : pointer(w)
 
-function run_bulkscan(method::Cint, Y, G, C, K, grid::Array{Float64, 1}; reml, prior_variance, prior_sample_size,
-                      optim_interval, decomp_scheme, h2_panel_mode = H2PANEL_REFERENCE, ctx = default_context())
+function run_bulkscan(method::Cint, Y, G, C, K, w, grid::Array{Float64, 1}; reml, prior_variance, prior_sample_size,
+                      optim_interval, decomp_scheme, h2_panel_mode = H2PANEL_REFERENCE, output_pvals = false,
+                      chisq_df = 1, ctx = default_context())
     (n, m) = size(Y); p = size(G, 2)
     U, lambda = decompose(K; decomp_scheme = decomp_scheme, ctx = ctx)
     L = Array{Float64, 2}(undef, p, m)
     H = method == METHOD_ALT_GRID ? Array{Float64, 2}(undef, p, m) : Array{Float64, 1}(undef, m)
-    prob = BlmmProblem(n, p, m, size(C, 2), pointer(Y), pointer(G), pointer(C), pointer(U), pointer(lambda))
+    P = output_pvals ? Array{Float64, 2}(undef, p, m) : Array{Float64, 2}(undef, 0, 0)
+    prob = BlmmProblem(n, p, m, size(C, 2), pointer(Y), pointer(G), pointer(C), pointer(U), pointer(lambda), wptr(w))
     opts = BlmmOpts(method, reml, prior_variance, prior_sample_size, pointer(grid), length(grid), optim_interval,
-                    h2_panel_mode, BLMM_MEM_HOST, 0)
-    GC.@preserve Y G C U lambda grid L H check(ctx, ccall((:blmm_bulkscan, libblmm), Cint,
+                    h2_panel_mode, BLMM_MEM_HOST, 0, output_pvals ? Int32(chisq_df) : Int32(0), Int32(0),
+                    output_pvals ? pointer(P) : Ptr{Float64}(C_NULL))
+    GC.@preserve Y G C U lambda w grid L H P check(ctx, ccall((:blmm_bulkscan, libblmm), Cint,
         (Ptr{Cvoid}, Ref{BlmmProblem}, Ref{BlmmOpts}, Ptr{Float64}, Ptr{Float64}), ctx.handle, prob, opts, L, H))
-    return L, H
+    return L, H, P
 end
+
+# NamedTuple assembly of src/bulkscan.jl:154-160 (p-values only on request)
+pack(names::NTuple{2, Symbol}, L, H, P, output_pvals, chisq_df) = output_pvals ?
+    NamedTuple{(names..., :log10Pvals_mat, :Chisq_df)}((L, H, P, chisq_df)) : NamedTuple{names}((L, H))
 
 # ---- bulkscan family (src/bulkscan.jl) ------------------------------------------------------------------
 function bulkscan_null_grid(Y::Array{Float64, 2}, G::Array{Float64, 2}, Covar::Array{Float64, 2},
                             K::Array{Float64, 2}, grid_list::Array{Float64, 1};
                             weights::Union{Missing, Array{Float64, 1}} = missing, addIntercept::Bool = true,
                             prior_variance::Float64 = 1.0, prior_sample_size::Float64 = 0.0, reml::Bool = false,
-                            decomp_scheme::String = "eigen")
-    Ys, Gs, Cs, Ks = prep(Y, G, Covar, K, weights, addIntercept)
-    L, h2 = run_bulkscan(METHOD_NULL_GRID, Ys, Gs, Cs, Ks, grid_list; reml = reml, prior_variance = prior_variance,
-                         prior_sample_size = prior_sample_size, optim_interval = 1, decomp_scheme = decomp_scheme)
-    return (L = L, h2_null_list = h2)
+                            decomp_scheme::String = "eigen", output_pvals::Bool = false, chisq_df::Int64 = 1)
+    Ys, Gs, Cs, Ks, w = prep(Y, G, Covar, K, weights, addIntercept)
+    L, h2, P = run_bulkscan(METHOD_NULL_GRID, Ys, Gs, Cs, Ks, w, grid_list; reml = reml, prior_variance = prior_variance,
+                            prior_sample_size = prior_sample_size, optim_interval = 1, decomp_scheme = decomp_scheme,
+                            output_pvals = output_pvals, chisq_df = chisq_df)
+    return pack((:L, :h2_null_list), L, h2, P, output_pvals, chisq_df)
 end
 bulkscan_null_grid(Y, G, K, grid_list; kw...) =
     bulkscan_null_grid(Y, G, ones(size(Y, 1), 1), K, grid_list; addIntercept = false, kw...)
 
 function bulkscan_alt_grid(Y::Array{Float64, 2}, G::Array{Float64, 2}, Covar::Array{Float64, 2},
-                           K::Array{Float64, 2}, hsq_list::Array{Float64, 1};
-                           weights::Union{Missing, Array{Float64, 1}} = missing, addIntercept::Bool = true,
-                           prior_variance::Float64 = 1.0, prior_sample_size::Float64 = 0.0, reml::Bool = false,
-                           decomp_scheme::String = "eigen")
-    Ys, Gs, Cs, Ks = prep(Y, G, Covar, K, weights, addIntercept)
-    L, h2_panel = run_bulkscan(METHOD_ALT_GRID, Ys, Gs, Cs, Ks, hsq_list; reml = reml, prior_variance = prior_variance,
-                               prior_sample_size = prior_sample_size, optim_interval = 1,
-                               decomp_scheme = decomp_scheme)
-    return (L = L, h2_panel = h2_panel)
+                            K::Array{Float64, 2}, hsq_list::Array{Float64, 1};
+                            weights::Union{Missing, Array{Float64, 1}} = missing, addIntercept::Bool = true,
+                            prior_variance::Float64 = 1.0, prior_sample_size::Float64 = 0.0, reml::Bool = false,
+                            decomp_scheme::String = "eigen", output_pvals::Bool = false, chisq_df::Int64 = 1)
+    Ys, Gs, Cs, Ks, w = prep(Y, G, Covar, K, weights, addIntercept)
+    L, h2, P = run_bulkscan(METHOD_ALT_GRID, Ys, Gs, Cs, Ks, w, hsq_list; reml = reml, prior_variance = prior_variance,
+                            prior_sample_size = prior_sample_size, optim_interval = 1, decomp_scheme = decomp_scheme,
+                            output_pvals = output_pvals, chisq_df = chisq_df)
+    return pack((:L, :h2_panel), L, h2, P, output_pvals, chisq_df)
 end
 bulkscan_alt_grid(Y, G, K, hsq_list; kw...) =
     bulkscan_alt_grid(Y, G, ones(size(Y, 1), 1), K, hsq_list; addIntercept = false, kw...)
@@ -162,12 +184,14 @@ function bulkscan_null(Y::Array{Float64, 2}, G::Array{Float64, 2}, Covar::Array{
                        nb::Int64 = Threads.nthreads(), nt_blas::Int64 = 1,   # CPU threading knobs: accepted, unused
                        weights::Union{Missing, Array{Float64, 1}} = missing, addIntercept::Bool = true,
                        prior_variance::Float64 = 1.0, prior_sample_size::Float64 = 0.0, reml::Bool = false,
-                       optim_interval::Int64 = 1, decomp_scheme::String = "eigen")
-    Ys, Gs, Cs, Ks = prep(Y, G, Covar, K, weights, addIntercept)
-    L, h2 = run_bulkscan(METHOD_NULL_EXACT, Ys, Gs, Cs, Ks, Float64[0.0]; reml = reml, prior_variance = prior_variance,
-                         prior_sample_size = prior_sample_size, optim_interval = optim_interval,
-                         decomp_scheme = decomp_scheme)
-    return (L = L, h2_null_list = h2)
+                       optim_interval::Int64 = 1, decomp_scheme::String = "eigen", output_pvals::Bool = false,
+                       chisq_df::Int64 = 1)
+    Ys, Gs, Cs, Ks, w = prep(Y, G, Covar, K, weights, addIntercept)
+    L, h2, P = run_bulkscan(METHOD_NULL_EXACT, Ys, Gs, Cs, Ks, w, Float64[0.0]; reml = reml,
+                            prior_variance = prior_variance, prior_sample_size = prior_sample_size,
+                            optim_interval = optim_interval, decomp_scheme = decomp_scheme,
+                            output_pvals = output_pvals, chisq_df = chisq_df)
+    return pack((:L, :h2_null_list), L, h2, P, output_pvals, chisq_df)
 end
 bulkscan_null(Y, G, K; kw...) = bulkscan_null(Y, G, ones(size(Y, 1), 1), K; addIntercept = false, kw...)
 
@@ -176,9 +200,11 @@ function bulkscan(Y::Array{Float64, 2}, G::Array{Float64, 2}, Covar::Array{Float
                   nb::Int64 = Threads.nthreads(), nt_blas::Int64 = 1,
                   weights::Union{Missing, Array{Float64, 1}} = missing, addIntercept::Bool = true,
                   prior_variance::Float64 = 1.0, prior_sample_size::Float64 = 0.0, reml::Bool = false,
-                  optim_interval::Int64 = 1, decomp_scheme::String = "eigen")
+                  optim_interval::Int64 = 1, decomp_scheme::String = "eigen", output_pvals::Bool = false,
+                  chisq_df::Int64 = 1)
     kw = (weights = weights, addIntercept = addIntercept, prior_variance = prior_variance,
-          prior_sample_size = prior_sample_size, reml = reml, decomp_scheme = decomp_scheme)
+          prior_sample_size = prior_sample_size, reml = reml, decomp_scheme = decomp_scheme,
+          output_pvals = output_pvals, chisq_df = chisq_df)
     if method == "null-exact"
         return bulkscan_null(Y, G, Covar, K; nb = nb, nt_blas = nt_blas, optim_interval = optim_interval, kw...)
     elseif method == "null-grid"
@@ -213,15 +239,15 @@ function scan(y::Array{Float64, 2}, g::Array{Float64, 2}, covar::Array{Float64, 
               decomp_scheme::String = "eigen", ctx::Context = default_context())
     assumption == "null" || throw(error("Assumption keyword is not supported. Please enter null or alt."))
     size(y, 2) == 1 || throw(error("Can only handle one trait."))
-    ys, gs, cs, Ks = prep(y, g, covar, K, weights, addIntercept)
+    ys, gs, cs, Ks, w = prep(y, g, covar, K, weights, addIntercept; ctx = ctx)
     (n, p) = size(gs)
     U, lambda = decompose(Ks; decomp_scheme = decomp_scheme, ctx = ctx)
     if !permutation_test        # scan_null, src/scan.jl:310-360
         lod = Array{Float64, 2}(undef, p, 1); s2 = Ref{Float64}(0.0); h2 = Ref{Float64}(0.0)
-        prob = BlmmProblem(n, p, 1, size(cs, 2), pointer(ys), pointer(gs), pointer(cs), pointer(U), pointer(lambda))
+        prob = BlmmProblem(n, p, 1, size(cs, 2), pointer(ys), pointer(gs), pointer(cs), pointer(U), pointer(lambda), wptr(w))
         opts = BlmmOpts(METHOD_NULL_EXACT, reml, prior_variance, prior_sample_size, C_NULL, 0, optim_interval,
                         H2PANEL_REFERENCE, BLMM_MEM_HOST, 0)
-        GC.@preserve ys gs cs U lambda lod check(ctx, ccall((:blmm_scan_null, libblmm), Cint,
+        GC.@preserve ys gs cs U lambda w lod check(ctx, ccall((:blmm_scan_null, libblmm), Cint,
             (Ptr{Cvoid}, Ref{BlmmProblem}, Ref{BlmmOpts}, Ptr{Float64}, Ref{Float64}, Ref{Float64}),
             ctx.handle, prob, opts, lod, s2, h2))
         return (sigma2_e = s2[], h2_null = h2[], lod = vec(lod))
@@ -229,10 +255,10 @@ function scan(y::Array{Float64, 2}, g::Array{Float64, 2}, covar::Array{Float64, 
     perm = permutation_indices(n, nperms, rndseed)
     lod = Array{Float64, 1}(undef, p); L_perms = Array{Float64, 2}(undef, p, nperms)
     maxlod = Array{Float64, 1}(undef, nperms); s2 = Ref{Float64}(0.0); h2 = Ref{Float64}(0.0)
-    prob = BlmmProblem(n, p, 1, size(cs, 2), pointer(ys), pointer(gs), pointer(cs), pointer(U), pointer(lambda))
+    prob = BlmmProblem(n, p, 1, size(cs, 2), pointer(ys), pointer(gs), pointer(cs), pointer(U), pointer(lambda), wptr(w))
     opts = BlmmOpts(METHOD_NULL_EXACT, reml, prior_variance, prior_sample_size, C_NULL, 0, optim_interval,
                     H2PANEL_REFERENCE, BLMM_MEM_HOST, 0)
-    GC.@preserve ys gs cs U lambda perm lod L_perms maxlod check(ctx, ccall((:blmm_scan_perms, libblmm), Cint,
+    GC.@preserve ys gs cs U lambda w perm lod L_perms maxlod check(ctx, ccall((:blmm_scan_perms, libblmm), Cint,
         (Ptr{Cvoid}, Ref{BlmmProblem}, Ref{BlmmOpts}, Ptr{Int32}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
          Ref{Float64}, Ref{Float64}), ctx.handle, prob, opts, perm, nperms, lod, L_perms, maxlod, s2, h2))
     return (sigma2_e = s2[], h2_null = h2[], lod = lod, L_perms = L_perms)
@@ -243,10 +269,27 @@ function scan(y::Array{Float64, 2}, g::Array{Float64, 2}, K::Array{Float64, 2}; 
 end
 scan(y::Array{Float64, 1}, g::Array{Float64, 2}, K::Array{Float64, 2}; kw...) = scan(reshape(y, :, 1), g, K; kw...)
 
-# src/analysis_helpers/single_trait_analysis.jl:13-23
-function get_thresholds(L::Array{Float64, 2}, signif_level::Array{Float64, 1})
-    thrs = map(x -> quantile(vec(maximum(L, dims = 1)), 1 - x), signif_level)
+# src/analysis_helpers/single_trait_analysis.jl:13-23: column maxima here, sort + type-7 quantiles on the device
+function get_thresholds(L::Array{Float64, 2}, signif_level::Array{Float64, 1}; ctx::Context = default_context())
+    return thresholds_from_max(vec(maximum(L, dims = 1)), signif_level; ctx = ctx)
+end
+
+# The same from the per-permutation maxima blmm_scan_perms already returns (no L_perms needed).
+function thresholds_from_max(maxlod::Array{Float64, 1}, signif_level::Array{Float64, 1}; ctx::Context = default_context())
+    thrs = Array{Float64, 1}(undef, length(signif_level))
+    GC.@preserve maxlod signif_level thrs check(ctx, ccall((:blmm_thresholds, libblmm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Cint),
+        ctx.handle, maxlod, length(maxlod), signif_level, length(signif_level), thrs, BLMM_MEM_HOST))
     return (probs = 1 .- signif_level, thrs = thrs)
+end
+
+# src/util.jl:199-206, elementwise on the device
+function lod2log10p(lod::Array{Float64}, df::Int64 = 1; ctx::Context = default_context())
+    out = similar(lod)
+    GC.@preserve lod out check(ctx, ccall((:blmm_lod2log10p, libblmm), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Cint, Ptr{Float64}, Cint),
+        ctx.handle, lod, length(lod), 1, 0, 0, df, out, BLMM_MEM_HOST))
+    return out
 end
 
 end # module

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define BLMM_ABI_VERSION 1
+#define BLMM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define BLMM_API __attribute__((visibility("default")))
@@ -84,6 +84,9 @@ typedef struct {
   const double* Covar;  /* n x c, column-major, ld = n (the shim builds [1 Covar] when addIntercept) */
   const double* U;      /* n x n, column a = a-th eigenvector of K  (Ut = U', src/transform_helpers.jl:24) */
   const double* lambda; /* n eigenvalues, matching U's columns */
+  const double* obs_weights; /* NULL, or n observation weights: the `weights` keyword.  Y, G and Covar are
+                           row-scaled by them on the device (src/bulkscan.jl:231-250, 351-370, 457-476;
+                           src/scan.jl:204-222); (U, lambda) must then decompose W*K*W (blmm_weight_kinship) */
 } blmm_problem;
 
 /* Keyword arguments shared by the entry points (defaults of src/bulkscan.jl:81-92 in comments). */
@@ -98,6 +101,10 @@ typedef struct {
   int32_t h2_panel_mode;     /* BLMM_H2PANEL_*                      (reference) */
   int32_t mem_space;         /* BLMM_MEM_* for problem + output pointers */
   int64_t ld_out;            /* leading dimension of p x m outputs; 0 => p */
+  int32_t chisq_df;          /* `output_pvals`/`chisq_df` keywords: 0 = no p-values; >= 1 = also write
+                                -log10 p of every LOD (lod2log10p, src/util.jl:199-206) to log10p_out (1) */
+  int32_t reserved;
+  double* log10p_out;        /* p x m (ld = ld_out or p), same memory space as the other outputs */
 } blmm_opts;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -168,6 +175,23 @@ BLMM_API int blmm_scan_perms(blmm_ctx* ctx, const blmm_problem* prob, const blmm
  * sqrt(w) without abs() as in scan_null.  lod_out: p x m, sigma2_out/h2_out: m.     */
 BLMM_API int blmm_scan_null(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* lod_out,
                    double* sigma2_out, double* h2_out);
+
+/* ---- post-processing ------------------------------------------------------------------------ */
+/* lod2log10p.(L, df), src/util.jl:199-206: out = -logccdf(Chisq(df), 2 ln10 lod) / ln10, elementwise over a
+ * rows x cols matrix (ld_in / ld_out leading dimensions, 0 => rows).  out may alias lod.            */
+BLMM_API int blmm_lod2log10p(blmm_ctx* ctx, const double* lod, int64_t rows, int64_t cols, int64_t ld_in,
+                    int64_t ld_out, int df, double* out, int mem_space);
+
+/* get_thresholds, src/analysis_helpers/single_trait_analysis.jl:13-23, from the per-permutation maximum
+ * LODs that blmm_scan_perms returns (maxlod_out): thrs_out[i] = quantile(maxlod, 1 - signif_level[i])
+ * (Julia's default quantile definition, type 7).  maxlod: nperms values in `mem_space`;
+ * signif_level / thrs_out: HOST arrays of nlev values.                                            */
+BLMM_API int blmm_thresholds(blmm_ctx* ctx, const double* maxlod, int64_t nperms, const double* signif_level,
+                    int nlev, double* thrs_out, int mem_space);
+
+/* K_st = W*K*W for observation weights w (src/bulkscan.jl:239, src/scan.jl:213): K_out[a,b] = w[a] K[a,b] w[b]. */
+BLMM_API int blmm_weight_kinship(blmm_ctx* ctx, int64_t n, const double* K, const double* w, double* K_out,
+                        int mem_space);
 
 #ifdef __cplusplus
 }

@@ -93,11 +93,35 @@ def make_perm_indices(n: int, nperms: int, rndseed: int = 0) -> np.ndarray:
     return rng.permuted(idx, axis=0)
 
 
+def _logccdf_chisq_tail(x: np.ndarray, df: int) -> np.ndarray:
+    """log Q(df/2, x/2) for large x, where chi2.logsf = log(sf) underflows to -inf (x > ~1480).
+    Q(a+1, y) = Q(a, y) + y^a e^-y / Gamma(a+1) in log space, from Q(1/2, y) = erfc(sqrt y) = 2 Phi(-sqrt(2y))
+    (log_ndtr keeps full accuracy in the tail) or Q(1, y) = e^-y."""
+    from scipy.special import gammaln, log_ndtr
+
+    y = 0.5 * np.asarray(x, dtype=np.float64)
+    if df % 2:
+        a, lq = 0.5, np.log(2.0) + log_ndtr(-np.sqrt(2.0 * y))
+    else:
+        a, lq = 1.0, -y
+    while a < 0.5 * df - 0.25:
+        lq = np.logaddexp(lq, a * np.log(y) - y - gammaln(a + 1.0))
+        a += 1.0
+    return lq
+
+
 def lod2log10p(lod, df: int = 1):
-    """src/util.jl:199-206: -logccdf(Chisq(df), 2 ln10 lod)/ln10."""
+    """src/util.jl:199-206: -logccdf(Chisq(df), 2 ln10 lod)/ln10.  Distributions.jl evaluates logccdf in log space;
+    scipy's logsf is log(sf) and underflows beyond LOD ~ 320, so the far tail is restated explicitly."""
     from scipy.stats import chi2
 
-    return -chi2.logsf(np.asarray(lod) * 2.0 * LN10, df) / LN10
+    x = np.asarray(lod, dtype=np.float64) * 2.0 * LN10
+    ls = np.asarray(chi2.logsf(x, df), dtype=np.float64)
+    far = np.isfinite(x) & (x > 1000.0)
+    if np.any(far):
+        ls = ls.copy()
+        ls[far] = _logccdf_chisq_tail(x[far], df)
+    return -ls / LN10
 
 
 def lod2p(lod, df: int = 1):

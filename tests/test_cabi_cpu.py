@@ -17,7 +17,8 @@ def declared_symbols():
 def test_header_declares_expected_surface():
     syms = declared_symbols()
     for must in ("blmm_create", "blmm_destroy", "blmm_last_error", "blmm_kinship", "blmm_decompose", "blmm_rotate",
-                 "blmm_bulkscan", "blmm_grid_loglik", "blmm_fit_h2", "blmm_scan_perms", "blmm_scan_null"):
+                 "blmm_bulkscan", "blmm_grid_loglik", "blmm_fit_h2", "blmm_scan_perms", "blmm_scan_null",
+                 "blmm_lod2log10p", "blmm_thresholds", "blmm_weight_kinship"):
         assert must in syms
 
 
@@ -27,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/blmm_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.blmm_abi_version() == 1
+    assert lib.blmm_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_no_cpu_fallback():
@@ -52,8 +53,21 @@ def test_product_does_not_import_oracle():
 
 
 def test_struct_layouts_match_header():
-    """blmm_problem / blmm_opts as the shim lays them out (9 and 11 eight-byte-aligned fields)."""
+    """blmm_problem / blmm_opts as the shims lay them out, checked against a C compile of the header."""
+    import subprocess
+    import tempfile
     from blmm_b200 import _lib
-    assert C.sizeof(_lib.Problem) == 9 * 8
-    assert C.sizeof(_lib.Opts) == 4 + 4 + 8 + 8 + 8 + 4 + 4 + 4 + 4 + 8
-    assert _lib.Opts.h2_grid.offset == 24 and _lib.Opts.ld_out.offset == 48
+    assert C.sizeof(_lib.Problem) == 10 * 8
+    assert C.sizeof(_lib.Opts) == 4 + 4 + 8 + 8 + 8 + 4 + 4 + 4 + 4 + 8 + 4 + 4 + 8
+    assert _lib.Opts.h2_grid.offset == 24 and _lib.Opts.ld_out.offset == 48 and _lib.Opts.log10p_out.offset == 64
+    src = """#include <stdio.h>
+#include <stddef.h>
+#include "blmm_b200.h"
+int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(blmm_problem), sizeof(blmm_opts), offsetof(blmm_problem, obs_weights),
+  offsetof(blmm_opts, h2_grid), offsetof(blmm_opts, ld_out), offsetof(blmm_opts, log10p_out)); return 0; }"""
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(x) for x in out] == [C.sizeof(_lib.Problem), C.sizeof(_lib.Opts), _lib.Problem.obs_weights.offset,
+                                     _lib.Opts.h2_grid.offset, _lib.Opts.ld_out.offset, _lib.Opts.log10p_out.offset]

@@ -1,0 +1,102 @@
+"""GPU parity of the post-processing entry points against the oracle:
+lod2log10p (src/util.jl:199-206), get_thresholds (src/analysis_helpers/single_trait_analysis.jl:13-23),
+observation weights crossing the ABI (src/bulkscan.jl:231-250, src/scan.jl:204-222)."""
+import numpy as np
+import pytest
+
+import blmm_oracle as orc
+from blmm_b200 import (bulkscan, bulkscan_alt_grid, bulkscan_null, bulkscan_null_grid, get_thresholds, lod2log10p, scan,
+                       synth, thresholds_from_max)
+
+pytestmark = pytest.mark.gpu
+GRID = np.arange(10) / 10.0
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+
+
+@pytest.mark.parametrize("df", [1, 2, 3, 4, 7])
+def test_lod2log10p_matches_chisq_logccdf(engine, df):
+    """From LOD 0 (p = 1) through tiny LODs to LOD 500 (p ~ 1e-500: the log-space form must not underflow)."""
+    lod = np.concatenate([[0.0, 1e-300, 1e-12, 1e-6, 1e-3], np.linspace(0.01, 2.0, 300), np.linspace(2.0, 60.0, 300),
+                          [100.0, 250.0, 500.0]])
+    got = lod2log10p(lod, df, engine=engine)
+    ref = orc.lod2log10p(lod, df)
+    assert got.shape == lod.shape
+    assert np.all(np.isfinite(got))
+    # relative to max(1, |ref|) as everywhere; and tight relative accuracy where the value is tiny
+    assert rel(got, ref) < 1e-10
+    big = ref > 1e-6
+    assert np.max(np.abs(got[big] - ref[big]) / ref[big]) < 1e-9
+
+
+def test_lod2log10p_matrix_and_kat(engine):
+    """test/scan_covar_test.jl:39-50 compares log10p output with lod2log10p.(L, 1); KAT: LOD of the 5 % chi-square(1)
+    critical value 3.841458820694124 is -log10(0.05)."""
+    rng = np.random.default_rng(5)
+    Lm = rng.gamma(1.0, 1.0, size=(37, 23))
+    got = lod2log10p(Lm, 1, engine=engine)
+    assert got.shape == Lm.shape and rel(got, orc.lod2log10p(Lm, 1)) < 1e-10
+    crit = 3.841458820694124 / (2 * np.log(10.0))
+    assert abs(lod2log10p(np.array([crit]), 1, engine=engine)[0] - (-np.log10(0.05))) < 1e-12
+
+
+def test_thresholds_type7_quantiles(engine):
+    rng = np.random.default_rng(11)
+    for nperms in (1, 2, 7, 1000, 10000):
+        mx = rng.gamma(2.0, 1.0, size=nperms)
+        sl = [0.1, 0.05, 0.01, 1.0, 0.0]
+        got = thresholds_from_max(mx, sl, engine=engine)
+        assert np.array_equal(got.thrs, np.quantile(mx, 1.0 - np.asarray(sl)))
+    Lp = rng.gamma(1.0, 1.0, size=(50, 300))
+    t = get_thresholds(Lp, [0.1, 0.05], engine=engine)
+    tr = orc.get_thresholds(Lp, [0.1, 0.05])
+    assert np.array_equal(t.thrs, tr["thrs"]) and np.array_equal(t.probs, tr["probs"])
+
+
+def test_observation_weights_all_methods(engine):
+    """weights= is applied on the device (row scaling folded into the rotation); the oracle pre-scales on the host
+    exactly as the reference does.  Own decomposition of W*K*W on both sides, so LODs (sign invariant) agree."""
+    Y, G, K = synth.make_problem(79, 150, 60, seed_g=21, seed_y=22)
+    rng = np.random.default_rng(3)
+    w = rng.uniform(0.5, 2.0, size=79)
+    Cv = synth.make_covar(79)[:, :2]
+    a = bulkscan_null_grid(Y, G, K, GRID, Covar=Cv, weights=w, engine=engine)
+    b = orc.bulkscan_null_grid(Y, G, K, GRID, Covar=Cv, weights=w)
+    assert np.array_equal(a.h2_null_list, b.h2_null_list) and rel(a.L, b.L) < 1e-8
+    a = bulkscan_alt_grid(Y, G, K, GRID, Covar=Cv, weights=w, engine=engine)
+    b = orc.bulkscan_alt_grid(Y, G, K, GRID, Covar=Cv, weights=w)
+    assert rel(a.L, b.L) < 1e-8
+    a = bulkscan_null(Y[:, :12], G, K, Covar=Cv, weights=w, reml=True, engine=engine)
+    b = orc.bulkscan_null(Y[:, :12], G, K, Covar=Cv, weights=w, reml=True)
+    assert np.max(np.abs(a.h2_null_list - b.h2_null_list)) < 1e-6
+    assert rel(a.L, b.L) < 2e-5  # LOD sensitivity to the 1e-6 Brent tolerance
+    s = scan(Y[:, 3], G, K, covar=Cv, weights=w, engine=engine)
+    r = orc.scan(Y[:, 3], G, K, covar=Cv, weights=w)
+    assert abs(s.h2_null - r["h2_null"]) < 1e-6 and rel(s.lod, r["lod"]) < 2e-5
+
+
+def test_weights_equal_prescaling_through_engine(engine):
+    """test/weighted_error_test.jl: scanning with weights == scanning pre-weighted inputs with K_st, no intercept added."""
+    Y, G, K = synth.make_problem(79, 90, 33, seed_g=31, seed_y=32)
+    w = np.random.default_rng(9).uniform(0.7, 1.4, size=79)
+    a = bulkscan_alt_grid(Y, G, K, GRID, weights=w, engine=engine)
+    Yw, Gw = w[:, None] * Y, w[:, None] * G
+    Kw = w[:, None] * K * w[None, :]
+    b = bulkscan_alt_grid(Yw, Gw, Kw, GRID, Covar=w[:, None], addIntercept=False, engine=engine)
+    assert rel(a.L, b.L) < 1e-9
+
+
+def test_output_pvals_fused(engine):
+    """output_pvals through blmm_opts.chisq_df for the three methods (src/bulkscan.jl:154-160)."""
+    Y, G, K = synth.make_problem(79, 130, 70, seed_g=41, seed_y=42)
+    for method in ("null-grid", "alt-grid", "null-exact"):
+        r = bulkscan(Y, G, K, method=method, output_pvals=True, chisq_df=1, engine=engine)
+        plain = bulkscan(Y, G, K, method=method, engine=engine)
+        assert np.array_equal(r.L, plain.L)
+        assert r.Chisq_df == 1
+        assert rel(r.log10Pvals_mat, orc.lod2log10p(np.maximum(plain.L, 0.0), 1)) < 1e-9
+    r2 = bulkscan(Y, G, K, method="null-grid", output_pvals=True, chisq_df=2, engine=engine)
+    assert rel(r2.log10Pvals_mat, orc.lod2log10p(np.maximum(r2.L, 0.0), 2)) < 1e-9
