@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libblmm_b200.so")
+# BLMM_B200_LIB (the variable the Julia shim reads too) points at another build of the same library
+LIB_PATH = os.environ.get("BLMM_B200_LIB") or os.path.join(HERE, "lib", "libblmm_b200.so")
 
 # status codes / enums of include/blmm_b200.h
 OK, E_INVALID, E_DIM, E_H2_ONE, E_ZERO_NORM, E_ONE_TRAIT, E_CUDA, E_NOT_SPD, E_NO_DEVICE, E_WEIGHTS = range(10)

@@ -15,10 +15,11 @@
 // sub-partition can saturate, so what costs time is every warp of a sub-partition leaving the DMMA
 // loop together (they consume the same stage and are served round-robin, so they run in lock step)
 // and the pipe idling through the epilogues.  The warps are therefore split into two groups
-// (marker rows 0-31 / 32-63 of the tile) that take turns in the DMMA loop, per sub-partition, through
-// a pair of named barriers: while one group multiplies, the other runs its epilogue (running-min
-// update, logarithm, stores) and the scalar FP64 work fills DMMA issue gaps instead of serialising
-// with it.
+// (marker rows 0-31 / 32-63 of the tile) that take turns in the DMMA loop, per sub-partition, by passing
+// a token through a pair of mbarriers: while one group multiplies, the other runs its epilogue
+// (running-min update, logarithm, stores) and the scalar FP64 work fills DMMA issue gaps instead of
+// serialising with it.  (bar.sync / bar.arrive pairs with a thread count do NOT order the groups on this
+// part: measured, both groups pass at once; tools/scratch notes in DESIGN.md.)
 #include <math.h>
 
 #include "blmm_kernels.cuh"
@@ -38,6 +39,21 @@ constexpr int GRID_MAX = 256;
 constexpr int LTAB = 512;  // entries of the in-kernel logarithm table
 
 static_assert(NWARPS == 16 && NTHREADS == 512, "ping-pong barrier counts assume 16 warps");
+
+// Development aid (tools/scan_timing.py builds a second library with -DBLMM_SCAN_TIMING): per-warp clock64
+// time in each phase of the kernel.  Not compiled into the product library.
+#ifdef BLMM_SCAN_TIMING
+__device__ long long g_scan_timing[256 * NWARPS * 8];
+__device__ long long g_scan_trace[NWARPS * 64 * 4];  // CTA 0: per warp, first 64 iterations: t(full), t(turn), t(dmma end), t(epi end)
+#define TCK(i)                      \
+  {                                 \
+    const long long t_now = clock64(); \
+    tacc[i] += t_now - tlast;       \
+    tlast = t_now;                  \
+  }
+#else
+#define TCK(i)
+#endif
 
 struct SmemPlan {
   int nstage;
@@ -66,13 +82,6 @@ __device__ __forceinline__ void dmma884_zero(double& c0, double& c1, double a, d
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};"
       : "=d"(c0), "=d"(c1)
       : "d"(a), "d"(b), "d"(0.0));
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // LOD = -(n/2) log10(v) for the final epilogue, ~8 FP64 operations (the FP64 pipe is shared with DMMA).
@@ -127,12 +136,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
   uint64_t* top_full = bars + 3;
   uint64_t* top_empty = bars + 4;
   int* rel_cnt = reinterpret_cast<int*>(bars + 5);  // [NS] consumers done with a stage
+  uint64_t* turn = bars + 8;                         // [4 sub-partitions][2 groups] ping-pong tokens
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   // The marker operand (all k) is re-read by every trait tile: ask L2 to keep it while the LOD /
   // h2 panels stream through (they are written with evict-first stores).
-  const uint64_t keep_policy = l2_evict_last_policy();
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
@@ -140,6 +149,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
     }
     mbar_init(top_full, 1);
     mbar_init(top_empty, NWARPS);
+    for (int i = 0; i < 8; ++i) mbar_init(&turn[i], 2);  // the two warps of the other group on the sub-partition
     mbar_fence_init();
   }
   {
@@ -157,8 +167,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
   }
   if (P.grid && tid < P.ngrid) grid_s[tid] = P.grid[tid];
   __syncthreads();
-  const double c_ln = -P.half_n * 0.43429448190325182765;
-  const double c_e = -P.half_n * 0.30102999566398119521;
 
   const int n_tiles = P.n_tiles_dev ? *P.n_tiles_dev : P.n_tiles_t;
   const int n_mt = P.p_pad / MT;
@@ -178,6 +186,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
     double* st = stages + (size_t)s * plan.stage_doubles;
     mbar_arrive_expect_tx(&full[s], stage_bytes);
     const double* src = P.Mop + (((size_t)(k0 + kk) * NQ) * P.p_pad + (size_t)mt * MT) * KC;
+    const uint64_t keep_policy = l2_evict_last_policy();
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
       bulk_g2s_hint(st + (size_t)q * MT * KC, src + (size_t)q * P.p_pad * KC, marker_chunk_bytes, &full[s], keep_policy);
@@ -212,15 +221,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
   const int aoff = (wm * 32 + g) * KC + t;
   const int boff = (wt * (8 * BT) + g) * KC + t;
   // Ping-pong: the two groups alternate in the DMMA loop, independently on every SM sub-partition
-  // (warps w, w+4 of a group share sub-partition w & 3).  Barrier 1 + 2*(w&3) + grp is "group grp may
-  // multiply"; 128 = the four warps of the sub-partition (two wait, two arrive).
-  const int my_turn = 1 + 2 * (warp & 3) + wm;
-  const int their_turn = 1 + 2 * (warp & 3) + (wm ^ 1);
-  if (wm == 1) named_bar_arrive(their_turn, 128);
+  // (warps w, w+4 of a group share sub-partition w & 3).  turn[2*(w&3) + grp] completes phase i when
+  // both warps of the other group have granted group grp its i-th turn.
+  uint64_t* my_turn = &turn[2 * (warp & 3) + wm];
+  uint64_t* their_turn = &turn[2 * (warp & 3) + (wm ^ 1)];
+  if (wm == 1 && lane == 0) mbar_arrive(their_turn);  // group 0 goes first
 
   int it = 0, s = 0;
   uint32_t sphase = 0;  // parity of the ring round
   int ntop = 0, cur_tt = -1;
+#ifdef BLMM_SCAN_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+#endif
   for (int u = u0; u < u1; ++u) {
     if (tt != cur_tt) {
       if (tid == 0) {
@@ -238,8 +251,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
       ++ntop;
       cur_tt = tt;
     }
+    TCK(5)
     const bool last_of_tt = (u + 1 == u1) || (mt + 1 == n_mt);
 
+    constexpr int VM = HAS_E ? 1 : 0;  // index multiplier: the one-k variants keep no running minimum
     double acc[4][BT][2];
     double vmin[HAS_E ? 4 : 1][BT][2];
     uint32_t cnt[HAS_E ? 2 * BT : 1];
@@ -250,17 +265,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
 
     for (int kk = 0; kk < nk; ++kk, ++it) {
       mbar_wait(&full[s], sphase);
+      TCK(0)
+#ifdef BLMM_SCAN_TIMING
+      if (blockIdx.x == 0 && lane == 0 && it >= 64 && it < 128) g_scan_trace[(warp * 64 + it - 64) * 4 + 0] = tlast;
+#endif
       const double* ms = stages + (size_t)s * plan.stage_doubles;
-      named_bar_sync(my_turn, 128);
+      // first fragments of the K loop, fetched before the turn starts
+      const double* ap = ms + aoff;
+      const double* bp = top + boff;
+      double af[2][4], bf[2][BT];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) af[0][a] = ap[a * 8 * KC];
+#pragma unroll
+      for (int b = 0; b < BT; ++b) bf[0][b] = bp[b * 8 * KC];
+      mbar_wait(my_turn, (uint32_t)it & 1u);
+      TCK(1)
+#ifdef BLMM_SCAN_TIMING
+      if (blockIdx.x == 0 && lane == 0 && it >= 64 && it < 128) g_scan_trace[(warp * 64 + it - 64) * 4 + 1] = tlast;
+#endif
       {
         // K loop, fully unrolled, fragments double-buffered in registers
-        const double* ap = ms + aoff;
-        const double* bp = top + boff;
-        double af[2][4], bf[2][BT];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) af[0][a] = ap[a * 8 * KC];
-#pragma unroll
-        for (int b = 0; b < BT; ++b) bf[0][b] = bp[b * 8 * KC];
 #pragma unroll
         for (int st = 0; st < NQ * (KC / 4); ++st) {
           const int cur = st & 1;
@@ -282,9 +306,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
             }
         }
       }
-      named_bar_arrive(their_turn, 128);
-      // per-k trait scalars for this lane's 2*BT trait columns
-      double ek[BT][2], etk[BT][2];
+      TCK(2)
+#ifdef BLMM_SCAN_TIMING
+      if (blockIdx.x == 0 && lane == 0 && it >= 64 && it < 128) g_scan_trace[(warp * 64 + it - 64) * 4 + 2] = tlast;
+#endif
+      // Still inside this group's turn: every scalar FP64 operation of the epilogue.  Issued while the
+      // other group multiplies they would sit behind its DMMA stream until it ends (measured: the pipe
+      // serves two back-to-back DMMA warps and starves a third warp's DFMA), so they go here, in the
+      // order the last k-step finishes the accumulators.  v overwrites the accumulator.
+      double ek[BT][2], etk[BT][2];  // per-k trait scalars for this lane's 2*BT trait columns
       {
         const double* sc = ms + (size_t)NQ * MT * KC + wt * (8 * BT) + 2 * t;
 #pragma unroll
@@ -299,11 +329,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
           etk[b][0] = w.x; etk[b][1] = w.y;
         }
       }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const double d = acc[a][b][cc];
+            acc[a][b][cc] = fma(-(d * d), etk[b][cc], ek[b][cc]);
+          }
+      // tmax! bookkeeping of this k: integer pipe only (strict `<` as `max .< to_compare`, on the bit
+      // patterns: equivalent for the non-negative v that occur; a negative v (r^2 > 1 by rounding)
+      // orders below every positive one, as it should)
+      auto update_min = [&]() {
+        if (HAS_E) {
+          const bool first = (kk == 0);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < BT; ++b)
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc) {
+                const double v = acc[a][b][cc];
+                const bool better = __double_as_longlong(v) < __double_as_longlong(vmin[a * VM][b][cc]);
+                const bool upd = first || better;
+                vmin[a * VM][b][cc] = upd ? v : vmin[a * VM][b][cc];
+                const int o = (a * BT + b) * 2 + cc;
+                const int sh = (o & 3) * 8;
+                if (ARGMAX) {
+                  if (upd) cnt[(o >> 2) * VM] = (cnt[(o >> 2) * VM] & ~(0xFFu << sh)) | ((uint32_t)kk << sh);
+                } else {
+                  if (better && !first) cnt[(o >> 2) * VM] += (1u << sh);
+                }
+              }
+        }
+      };
+      const bool last_k = (kk == nk - 1);
+      if (last_k) {
+        // last k of the unit: one logarithm per output; the LOD replaces the accumulator
+        update_min();
+        const double c_ln = -P.half_n * 0.43429448190325182765;
+        const double c_e = -P.half_n * 0.30102999566398119521;
+        bool special = false;
+        double lod[4][BT][2];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < BT; ++b)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+              lod[a][b][cc] = fast_lod(HAS_E ? vmin[a * VM][b][cc] : acc[a][b][cc], logtab, c_ln, c_e, special);
+        if (__any_sync(0xffffffffu, special)) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < BT; ++b)
+#pragma unroll
+              for (int cc = 0; cc < 2; ++cc)
+                lod[a][b][cc] = fix_lod(HAS_E ? vmin[a * VM][b][cc] : acc[a][b][cc], lod[a][b][cc]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < BT; ++b)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) acc[a][b][cc] = lod[a][b][cc];
+      }
+      // the FP64 work above is issued before the turn is handed over
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < BT; ++b) asm volatile("" ::"d"(acc[a][b][0]), "d"(acc[a][b][1]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(their_turn);
       // Release the stage.  The last of the NWARPS consumers refills it at once with the operands
       // of iteration it + NS, so the copy is in flight as early as the ring allows.
-      __syncwarp();
       if (lane == 0) {
-        if (last_of_tt && kk == nk - 1) mbar_arrive(top_empty);
+        if (last_of_tt && last_k) mbar_arrive(top_empty);
         __threadfence_block();
         if (atomicAdd(&rel_cnt[s], 1) == NWARPS - 1) {
           rel_cnt[s] = 0;
@@ -318,63 +420,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
         s = 0;
         sphase ^= 1u;
       }
-
-      if (HAS_E) {
-        const bool first = (kk == 0);
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < BT; ++b)
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              const double d = acc[a][b][cc];
-              const double v = fma(-(d * d), etk[b][cc], ek[b][cc]);
-              // strict `<` as `max .< to_compare` in tmax!, on the bit patterns (integer pipe; the
-              // FP64 pipe is the bottleneck).  Equivalent for the non-negative v that occur; a
-              // negative v (r^2 > 1 by rounding) orders below every positive one, as it should.
-              const bool better = __double_as_longlong(v) < __double_as_longlong(vmin[a][b][cc]);
-              const bool upd = first || better;
-              vmin[a][b][cc] = upd ? v : vmin[a][b][cc];
-              const int o = (a * BT + b) * 2 + cc;
-              const int sh = (o & 3) * 8;
-              if (ARGMAX) {
-                if (upd) cnt[o >> 2] = (cnt[o >> 2] & ~(0xFFu << sh)) | ((uint32_t)kk << sh);
-              } else {
-                if (better && !first) cnt[o >> 2] += (1u << sh);
-              }
-            }
-      } else {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < BT; ++b)
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              const double d = acc[a][b][cc];
-              acc[a][b][cc] = fma(-(d * d), etk[b][cc], 1.0);
-            }
-      }
+      if (!last_k) update_min();
+      TCK(3)
+#ifdef BLMM_SCAN_TIMING
+      if (blockIdx.x == 0 && lane == 0 && it >= 64 && it < 128) g_scan_trace[(warp * 64 + it - 64) * 4 + 3] = tlast;
+#endif
     }
 
-    // final epilogue: one logarithm per output, streaming stores
-    bool special = false;
-    double lod[4][BT][2];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < BT; ++b)
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc)
-          lod[a][b][cc] = fast_lod(HAS_E ? vmin[a][b][cc] : acc[a][b][cc], logtab, c_ln, c_e, special);
-    if (__any_sync(0xffffffffu, special)) {
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < BT; ++b)
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc)
-            lod[a][b][cc] = fix_lod(HAS_E ? vmin[a][b][cc] : acc[a][b][cc], lod[a][b][cc]);
-    }
+    // stores of the unit (LOD in the accumulator registers), outside the turn
     const int kbase = (HAS_E && ARGMAX && P.tile_k0) ? P.tile_k0[tt] : 0;
     const int row0 = mt * MT + wm * 32 + g;
     const bool full_rows = (mt + 1) * MT <= P.p;  // every marker row of the tile exists
@@ -407,13 +460,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
         if (full_rows) {
           if (Lc) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a) st_stream(Lc + a * 8, lod[a][b][cc]);
+            for (int a = 0; a < 4; ++a) st_stream(Lc + a * 8, acc[a][b][cc]);
           }
           if (HAS_E && Hc) {
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
               const int o = (a * BT + b) * 2 + cc;
-              const int cv = (int)((cnt[o >> 2] >> ((o & 3) * 8)) & 0xFFu);
+              const int cv = (int)((cnt[(o >> 2) * VM] >> ((o & 3) * 8)) & 0xFFu);
               st_stream(Hc + a * 8, grid_s[kbase + cv]);
             }
           }
@@ -421,19 +474,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
             if (row0 + a * 8 < P.p) {
-              if (Lc) st_stream(Lc + a * 8, lod[a][b][cc]);
+              if (Lc) st_stream(Lc + a * 8, acc[a][b][cc]);
               if (HAS_E && Hc) {
                 const int o = (a * BT + b) * 2 + cc;
-                const int cv = (int)((cnt[o >> 2] >> ((o & 3) * 8)) & 0xFFu);
+                const int cv = (int)((cnt[(o >> 2) * VM] >> ((o & 3) * 8)) & 0xFFu);
                 st_stream(Hc + a * 8, grid_s[kbase + cv]);
               }
             } else {
-              lod[a][b][cc] = 0.0;  // padded marker rows stay out of the column maximum
+              acc[a][b][cc] = 0.0;  // padded marker rows stay out of the column maximum
             }
           }
         }
         if (COLMAX) {
-          double cmax = fmax(fmax(lod[0][b][cc], lod[1][b][cc]), fmax(lod[2][b][cc], lod[3][b][cc]));
+          double cmax = fmax(fmax(acc[0][b][cc], acc[1][b][cc]), fmax(acc[2][b][cc], acc[3][b][cc]));
           cmax = fmax(cmax, 0.0);
           cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, 4));
           cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, 8));
@@ -445,9 +498,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
       mt = 0;
       ++tt;
     }
+    TCK(4)
   }
-  // consume the other group's last "your turn" so that no barrier is left half-complete at exit
-  if (wm == 0) named_bar_sync(my_turn, 128);
+#ifdef BLMM_SCAN_TIMING
+  if (lane == 0 && blockIdx.x < 256)
+    for (int i = 0; i < 8; ++i) g_scan_timing[((size_t)blockIdx.x * NWARPS + warp) * 8 + i] = tacc[i];
+#endif
 }
 
 __global__ void logtab_kernel(double* tab) {
@@ -490,8 +546,6 @@ void launch_nq(const ScanParams& P, int sm_count, cudaStream_t stream) {
 
 }  // namespace
 
-int launch_scan_v3(const ScanParams& P, int sm_count, cudaStream_t stream);  // blmm_scan_v3.cu (A/B only)
-
 int scan_max_nq(int nk) {
   (void)nk;
   return 5;
@@ -504,12 +558,16 @@ int launch_logtab(double* tab, cudaStream_t stream) {
   return 1;
 }
 
+#ifdef BLMM_SCAN_TIMING
+extern "C" __attribute__((visibility("default"))) int blmm_debug_scan_timing(long long* out, int nblocks) {
+  return (int)cudaMemcpyFromSymbol(out, g_scan_timing, sizeof(long long) * (size_t)nblocks * NWARPS * 8);
+}
+extern "C" __attribute__((visibility("default"))) int blmm_debug_scan_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_scan_trace, sizeof(g_scan_trace));
+}
+#endif
+
 int launch_scan(const ScanParams& P, int sm_count, cudaStream_t stream) {
-  static const bool use_v3 = [] {
-    const char* v = getenv("BLMM_SCAN_KERNEL");
-    return v && v[0] == 'v' && v[1] == '3';
-  }();
-  if (use_v3) return launch_scan_v3(P, sm_count, stream);
   if ((!P.e && P.nk != 1) || (P.e && P.colmax)) return 0;  // combinations the kernel variants do not cover
   switch (P.nq) {
     case 1: launch_nq<1>(P, sm_count, stream); break;

@@ -1,0 +1,157 @@
+// Microbenchmark of the scan kernel's inner loop in isolation: DMMA.8x8x4 fed from shared memory with the
+// [row][KC=20] fragment layout, K = 80 per iteration, accumulators restarted every iteration, no TMA, no
+// barriers, optional alt-grid style per-k epilogue.  Reports TFLOP/s (2*8*8*4 flop per DMMA) per variant so
+// the kernel's DMMA-pipe ceiling can be separated from its pipeline (stage waits, epilogue) losses.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/dmma_loop tools/dmma_loop.cu
+#include <cstdio>
+#include <algorithm>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void dmma0(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};" : "=d"(c0), "=d"(c1) : "d"(a), "d"(b), "d"(0.0));
+}
+
+constexpr int KC = 20, NQ = 4, MT = 64, TT = 128;
+
+// AM x BN atoms per warp; EPI: 0 none, 1 = per-iteration running-min epilogue (2 FP64 ops + integer compare);
+// BOUT: trait atoms are the outer DMMA loop (A fragment changes fastest) instead of the inner one.
+template <int AM, int BN, int EPI, bool BOUT>
+__global__ void __launch_bounds__(AM * BN >= 16 ? 256 : 512, 1) loop_kernel(double* out, int iters, const double* et_g) {
+  extern __shared__ double sm[];
+  double* sa = sm;                    // [NQ][MT][KC]
+  double* sb = sm + NQ * MT * KC;     // [NQ][TT][KC]
+  for (int i = threadIdx.x; i < NQ * MT * KC; i += blockDim.x) sa[i] = 1e-3 * (i % 97);
+  for (int i = threadIdx.x; i < NQ * TT * KC; i += blockDim.x) sb[i] = 1e-4 * (i % 89);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = warp % (MT / (8 * AM)), wt = (warp / (MT / (8 * AM))) % (TT / (8 * BN));
+  const double* ap = sa + (wm * 8 * AM + g) * KC + t;
+  const double* bp = sb + (wt * 8 * BN + g) * KC + t;
+  double c[AM][BN][2], vmin[AM][BN][2];
+  const double et = et_g[lane], e = et_g[32 + lane];
+#pragma unroll
+  for (int a = 0; a < AM; ++a)
+#pragma unroll
+    for (int b = 0; b < BN; ++b) vmin[a][b][0] = vmin[a][b][1] = 1e300;
+  for (int it = 0; it < iters; ++it) {
+    double af[2][AM], bf[2][BN];
+#pragma unroll
+    for (int a = 0; a < AM; ++a) af[0][a] = ap[a * 8 * KC];
+#pragma unroll
+    for (int b = 0; b < BN; ++b) bf[0][b] = bp[b * 8 * KC];
+#pragma unroll
+    for (int st = 0; st < NQ * (KC / 4); ++st) {
+      const int cur = st & 1;
+      if (st + 1 < NQ * (KC / 4)) {
+        const int q1 = (st + 1) / (KC / 4), s1 = (st + 1) % (KC / 4);
+#pragma unroll
+        for (int a = 0; a < AM; ++a) af[cur ^ 1][a] = ap[q1 * (MT * KC) + a * 8 * KC + s1 * 4];
+#pragma unroll
+        for (int b = 0; b < BN; ++b) bf[cur ^ 1][b] = bp[q1 * (TT * KC) + b * 8 * KC + s1 * 4];
+      }
+      if (BOUT) {
+#pragma unroll
+        for (int b = 0; b < BN; ++b)
+#pragma unroll
+          for (int a = 0; a < AM; ++a) {
+            if (st == 0) dmma0(c[a][b][0], c[a][b][1], af[cur][a], bf[cur][b]);
+            else dmma(c[a][b][0], c[a][b][1], af[cur][a], bf[cur][b]);
+          }
+      } else {
+#pragma unroll
+        for (int a = 0; a < AM; ++a)
+#pragma unroll
+          for (int b = 0; b < BN; ++b) {
+            if (st == 0) dmma0(c[a][b][0], c[a][b][1], af[cur][a], bf[cur][b]);
+            else dmma(c[a][b][0], c[a][b][1], af[cur][a], bf[cur][b]);
+          }
+      }
+    }
+    if (EPI) {
+#pragma unroll
+      for (int a = 0; a < AM; ++a)
+#pragma unroll
+        for (int b = 0; b < BN; ++b)
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            const double d = c[a][b][cc];
+            const double v = fma(-(d * d), et, e);
+            const bool better = __double_as_longlong(v) < __double_as_longlong(vmin[a][b][cc]);
+            vmin[a][b][cc] = better ? v : vmin[a][b][cc];
+          }
+    } else {
+#pragma unroll
+      for (int a = 0; a < AM; ++a)
+#pragma unroll
+        for (int b = 0; b < BN; ++b) {
+          vmin[a][b][0] = fmin(vmin[a][b][0], c[a][b][0] * 0.0 + vmin[a][b][0]);  // keep c live, ~free
+        }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int a = 0; a < AM; ++a)
+#pragma unroll
+    for (int b = 0; b < BN; ++b) s += vmin[a][b][0] + vmin[a][b][1] + c[a][b][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+template <typename F>
+float time_ms(F&& launch, int reps = 5) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  launch();
+  cudaDeviceSynchronize();
+  float best = 1e30f;
+  for (int r = 0; r < reps; ++r) {
+    cudaEventRecord(e0);
+    launch();
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    best = std::min(best, ms);
+  }
+  return best;
+}
+
+template <int AM, int BN, int EPI, bool BOUT>
+void run(const char* name, int warps, int sms, double* out, const double* et) {
+  const int iters = 2000;
+  const size_t smem = (size_t)(NQ * MT * KC + NQ * TT * KC) * 8;
+  cudaFuncSetAttribute(loop_kernel<AM, BN, EPI, BOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  float ms = time_ms([&] { loop_kernel<AM, BN, EPI, BOUT><<<sms, warps * 32, smem>>>(out, iters, et); });
+  const double flop = (double)sms * warps * iters * 20.0 * AM * BN * 512.0;
+  printf("{\"variant\": \"%s\", \"warps\": %d, \"ms\": %.3f, \"tflops\": %.2f}\n", name, warps, ms, flop / (ms * 1e-3) / 1e12);
+}
+
+int main() {
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, 0);
+  const int sms = prop.multiProcessorCount;
+  double *out, *et;
+  cudaMalloc(&out, 1024);
+  cudaMalloc(&et, 64 * 8);
+  double h[64];
+  for (int i = 0; i < 64; ++i) h[i] = i < 32 ? 1e-6 : 1.0;
+  cudaMemcpy(et, h, sizeof(h), cudaMemcpyHostToDevice);
+  run<4, 2, 0, false>("4x2", 16, sms, out, et);
+  run<4, 2, 0, false>("4x2", 8, sms, out, et);
+  run<4, 2, 0, false>("4x2", 4, sms, out, et);
+  run<4, 2, 0, true>("4x2 b-outer", 16, sms, out, et);
+  run<4, 2, 0, true>("4x2 b-outer", 8, sms, out, et);
+  run<2, 4, 0, false>("2x4", 16, sms, out, et);
+  run<2, 4, 0, false>("2x4", 8, sms, out, et);
+  run<4, 4, 0, false>("4x4", 8, sms, out, et);
+  run<4, 4, 0, false>("4x4", 4, sms, out, et);
+  run<4, 4, 0, true>("4x4 b-outer", 8, sms, out, et);
+  run<2, 2, 0, false>("2x2", 16, sms, out, et);
+  run<4, 2, 1, false>("4x2 +epi", 16, sms, out, et);
+  run<4, 2, 1, false>("4x2 +epi", 8, sms, out, et);
+  run<4, 4, 1, false>("4x4 +epi", 8, sms, out, et);
+  return 0;
+}

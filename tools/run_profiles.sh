@@ -1,3 +1,5 @@
+# Round-1 evidence run on one B200: bench lines (ours + reference arm), launch list and ncu captures of the
+# dominant kernels.  Outputs land in gpurun_out/; summaries are copied to profiles/ by tools/collect_profiles.sh.
 set -x
 python bench.py > gpurun_out/bench_r01.json 2> gpurun_out/bench_r01.err; echo rc=$?
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r01.json 2> gpurun_out/bench_ref_r01.err; echo rc=$?
