@@ -16,7 +16,7 @@ LIBDIR = os.path.join(HERE, "blmm_b200", "lib")
 LIB = os.path.join(LIBDIR, "libblmm_b200.so")
 SOURCES = ["blmm_api.cu", "blmm_prep.cu", "blmm_fit.cu", "blmm_scan.cu", "blmm_scan_stream.cu", "blmm_post.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-pthread"]
 
 
 def _stale(target: str, deps: list[str]) -> bool:
@@ -47,7 +47,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcusolver", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcusolver", "-lpthread", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         subprocess.run(cmd, check=True)
     return LIB
 

@@ -9,7 +9,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/blmm_b200.h"
@@ -21,7 +23,7 @@ using namespace blmm;
 enum Slot {
   S_Y_IN, S_G_IN, S_C_IN, S_U_IN, S_LAM, S_GRID, S_Y0, S_C0, S_G0, S_YR, S_W, S_SW, S_Q, S_SLW, S_LDS,
   S_ELL, S_RSS, S_BEST, S_ELLMAX, S_MOP, S_TOP, S_E, S_ET, S_BINS, S_TILEK0, S_COLMAP, S_L, S_H2P, S_H2V,
-  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_LOGTAB, S_XOP, S_DYINV, S_PVAL, S_OBSW, S_UW, S_SORT, S_SORTTMP, S_PROBS,
+  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_LOGTAB, S_XOP, S_DYINV, S_PVAL, S_OBSW, S_UW, S_SORT, S_SORTTMP, S_PROBS, S_H2IDX,
   S_COUNT
 };
 
@@ -31,6 +33,9 @@ struct blmm_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap the scan (host-buffer calls)
   cudaEvent_t chunk_ev[16] = {};
+  cudaEvent_t copied_ev[16] = {};      // chunk's index panel has landed in h_idx
+  uint8_t* h_idx = nullptr;            // pinned staging of the h2 index panel (host-buffer alt-grid calls)
+  size_t h_idx_cap = 0;
   cusolverDnHandle_t solver = nullptr;
   void* buf[S_COUNT] = {};
   size_t cap[S_COUNT] = {};
@@ -308,31 +313,94 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   if (ms == BLMM_MEM_HOST && alt && P.n_tiles_t >= 16 && o->chisq_df <= 0) {
     // Host-buffer alt-grid: the p x m panels (2 x 2 GB at BXD size) leave over PCIe, which takes ~5x
     // the scan itself.  Scan the trait tiles in chunks and copy each chunk's columns back on a
-    // second stream while the next chunk is scanned.
+    // second stream while the next chunk is scanned.  The h2 panel holds one of <= 255 grid values per
+    // entry, so it crosses PCIe as one-byte grid indices (1/8 of the bytes) into pinned staging and is
+    // expanded to grid[index] in the caller's Float64 array by host threads while later chunks copy.
     const int nchunk = 8;
     const int n_tiles = P.n_tiles_t;
+    const bool idx_panel = dH && P.nq <= scan_max_nq(P.nk);
+    uint8_t* dI = nullptr;
+    if (idx_panel) {
+      dI = ws<uint8_t>(ctx, S_H2IDX, (size_t)p * m);
+      if (ctx->h_idx_cap < (size_t)p * m) {
+        if (ctx->h_idx) CUDA_TRY(cudaFreeHost(ctx->h_idx));
+        ctx->h_idx = nullptr;
+        ctx->h_idx_cap = 0;
+        CUDA_TRY(cudaMallocHost(&ctx->h_idx, (size_t)p * m));
+        ctx->h_idx_cap = (size_t)p * m;
+      }
+    }
+    int64_t cbeg[nchunk + 1];
+    for (int ch = 0; ch <= nchunk; ++ch)
+      cbeg[ch] = std::min<int64_t>((int64_t)((int64_t)n_tiles * ch / nchunk) * SCAN_TT, m);
+    // expansion workers: worker w takes its slice of the columns of every chunk as the chunk lands
+    struct Expander {
+      std::vector<std::thread> th;
+      std::atomic<int> ready{0};
+      std::atomic<bool> abort{false};
+      ~Expander() {
+        abort.store(true);
+        for (auto& t : th) t.join();
+      }
+    } ex;
+    if (idx_panel) {
+      const unsigned hc = std::thread::hardware_concurrency();
+      const int W = (int)std::max(1u, std::min(16u, hc > 1 ? hc - 1 : 1u));
+      const uint8_t* hI = ctx->h_idx;
+      const double* grid = o->h2_grid;
+      for (int w = 0; w < W; ++w)
+        ex.th.emplace_back([&ex, w, W, hI, grid, h2_out, p, ld, &cbeg, nchunk]() {
+          for (int ch = 0; ch < nchunk; ++ch) {
+            while (ex.ready.load(std::memory_order_acquire) <= ch) {
+              if (ex.abort.load()) return;
+              std::this_thread::yield();
+            }
+            const int64_t c0 = cbeg[ch], c1 = cbeg[ch + 1];
+            const int64_t a = c0 + (c1 - c0) * w / W, b = c0 + (c1 - c0) * (w + 1) / W;
+            for (int64_t col = a; col < b; ++col) {
+              const uint8_t* src = hI + col * p;
+              double* dst = h2_out + col * ld;
+              for (int64_t i = 0; i < p; ++i) dst[i] = grid[src[i]];
+            }
+          }
+        });
+    }
     for (int ch = 0; ch < nchunk; ++ch) {
       const int t0 = (int)((int64_t)n_tiles * ch / nchunk), t1 = (int)((int64_t)n_tiles * (ch + 1) / nchunk);
-      const int64_t c0 = (int64_t)t0 * SCAN_TT, c1 = std::min<int64_t>((int64_t)t1 * SCAN_TT, m);
+      const int64_t c0 = cbeg[ch], c1 = cbeg[ch + 1];
       ScanParams Pc = P;
-      Pc.Top = P.Top + c0 * KC;
-      Pc.e = P.e + c0;
-      Pc.et = P.et + c0;
+      Pc.Top = P.Top + (int64_t)t0 * SCAN_TT * KC;
+      Pc.e = P.e + (int64_t)t0 * SCAN_TT;
+      Pc.et = P.et + (int64_t)t0 * SCAN_TT;
       Pc.L = dL + c0 * p;
-      Pc.H2 = dH ? dH + c0 * p : nullptr;
+      Pc.H2 = (dH && !idx_panel) ? dH + c0 * p : nullptr;
+      Pc.H2idx = idx_panel ? dI + c0 * p : nullptr;
       Pc.m = m - c0;
       Pc.n_tiles_t = t1 - t0;
       run_scan(ctx, Pc);
       CUDA_TRY(cudaEventRecord(ctx->chunk_ev[ch], ctx->stream));
       CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[ch], 0));
+      if (idx_panel) {
+        // indices first: their expansion then overlaps the (8x larger) copy of the chunk's LOD columns
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_idx + c0 * p, dI + c0 * p, (size_t)(c1 - c0) * p, cudaMemcpyDeviceToHost,
+                                 ctx->copy_stream));
+        CUDA_TRY(cudaEventRecord(ctx->copied_ev[ch], ctx->copy_stream));
+      }
       CUDA_TRY(cudaMemcpy2DAsync(L_out + c0 * ld, ld * sizeof(double), dL + c0 * p, p * sizeof(double),
                                  p * sizeof(double), c1 - c0, cudaMemcpyDeviceToHost, ctx->copy_stream));
-      if (dH)
+      if (dH && !idx_panel)
         CUDA_TRY(cudaMemcpy2DAsync(h2_out + c0 * ld, ld * sizeof(double), dH + c0 * p, p * sizeof(double),
                                    p * sizeof(double), c1 - c0, cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
+    if (idx_panel)
+      for (int ch = 0; ch < nchunk; ++ch) {
+        CUDA_TRY(cudaEventSynchronize(ctx->copied_ev[ch]));
+        ex.ready.store(ch + 1, std::memory_order_release);
+      }
     finish_and_check(ctx);
     CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    for (auto& t : ex.th) t.join();
+    ex.th.clear();
     return BLMM_OK;
   }
   run_scan(ctx, P);
@@ -798,7 +866,9 @@ int blmm_create(blmm_ctx** out, int device) {
             cudaMalloc(&ctx->d_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaMallocHost(&ctx->h_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
-  for (int i = 0; ok && i < 16; ++i) ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < 16; ++i)
+    ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->copied_ev[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     blmm_destroy(ctx);
     return BLMM_E_CUDA;
@@ -815,11 +885,14 @@ void blmm_destroy(blmm_ctx* ctx) {
     if (ctx->buf[s]) cudaFree(ctx->buf[s]);
   if (ctx->d_flags) cudaFree(ctx->d_flags);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->h_idx) cudaFreeHost(ctx->h_idx);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  for (int i = 0; i < 16; ++i)
+  for (int i = 0; i < 16; ++i) {
     if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+    if (ctx->copied_ev[i]) cudaEventDestroy(ctx->copied_ev[i]);
+  }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

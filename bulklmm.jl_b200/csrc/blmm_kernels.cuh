@@ -122,6 +122,8 @@ struct ScanParams {
   double* L0;              // if non-null: output column 0 goes here (length p) and column s >= 1 goes to
                            // column s-1 of L / colmax (scan_perms_lite's lod vs L_perms split, src/scan.jl:545-546)
   double* H2;              // p x m h2 panel, ld = ldL (nullptr => not stored)
+  uint8_t* H2idx;          // p x m panel of grid INDICES (h2 = grid[index]), ld = p, one byte each (nullptr => not
+                           // stored): what host-buffer calls bring back over PCIe instead of 8-byte values
   double* colmax;          // [m] max over markers per output column (nullptr => off); caller zero-fills
   int64_t ldL;
   int nq;                  // K-chunks (ceil(n / KC))

@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
         double* Lc = nullptr;
         double* Hc = nullptr;
         double* Mc = nullptr;
+        uint8_t* Ic = nullptr;
         if (col >= 0) {
           if (P.L0) {
             if (col == 0) {
@@ -456,6 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
             if (COLMAX) Mc = P.colmax + col;
           }
           if (HAS_E && P.H2) Hc = P.H2 + col * P.ldL + row0;
+          if (HAS_E && P.H2idx) Ic = P.H2idx + col * (int64_t)P.p + row0;
         }
         if (full_rows) {
           if (Lc) {
@@ -470,15 +472,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
               st_stream(Hc + a * 8, grid_s[kbase + cv]);
             }
           }
+          if (HAS_E && Ic) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              const int o = (a * BT + b) * 2 + cc;
+              Ic[a * 8] = (uint8_t)(kbase + (int)((cnt[(o >> 2) * VM] >> ((o & 3) * 8)) & 0xFFu));
+            }
+          }
         } else {
 #pragma unroll
           for (int a = 0; a < 4; ++a) {
             if (row0 + a * 8 < P.p) {
               if (Lc) st_stream(Lc + a * 8, acc[a][b][cc]);
-              if (HAS_E && Hc) {
+              if (HAS_E && (Hc || Ic)) {
                 const int o = (a * BT + b) * 2 + cc;
                 const int cv = (int)((cnt[(o >> 2) * VM] >> ((o & 3) * 8)) & 0xFFu);
-                st_stream(Hc + a * 8, grid_s[kbase + cv]);
+                if (Hc) st_stream(Hc + a * 8, grid_s[kbase + cv]);
+                if (Ic) Ic[a * 8] = (uint8_t)(kbase + cv);
               }
             } else {
               acc[a][b][cc] = 0.0;  // padded marker rows stay out of the column maximum

@@ -174,3 +174,21 @@ def test_alt_grid_host_chunked_copyback(engine):
     assert rel(a.L, ref.L) < 1e-8
     assert np.mean(a.h2_panel != ref.h2_panel) < 1e-4
     assert np.all(np.isin(a.h2_panel, GRID))
+    # The host path brings the h2 panel back as one-byte grid indices and expands them with host threads; the
+    # device-resident path stores Float64 grid values from the kernel.  Same call, both ways: identical bits.
+    import torch
+    from blmm_b200 import _lib as L
+    dev = torch.device("cuda:0")
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64).T)).to(dev)
+    n, p, m = 79, 70, 2101
+    for mode, name in ((L.H2PANEL_REFERENCE, "reference"), (L.H2PANEL_ARGMAX, "argmax")):
+        host = bulkscan_alt_grid(Y, G, K, GRID, decomposition=dec, engine=engine, h2_panel_mode=name)
+        d = [t(Y), t(G), t(np.ones((n, 1))), t(dec[0]), torch.from_numpy(lam.copy()).to(dev)]
+        dL = torch.empty((m, p), dtype=torch.float64, device=dev)
+        dH = torch.empty((m, p), dtype=torch.float64, device=dev)
+        pr = engine.make_problem(n, p, m, 1, *[x.data_ptr() for x in d])
+        o, keep = engine.make_opts(method=L.METHOD_ALT_GRID, h2_grid=GRID, mem_space=L.MEM_DEVICE, h2_panel_mode=mode)
+        engine.bulkscan_raw(pr, o, dL.data_ptr(), dH.data_ptr())
+        engine.sync()
+        assert np.array_equal(host.L, dL.cpu().numpy().T)
+        assert np.array_equal(host.h2_panel, dH.cpu().numpy().T)
