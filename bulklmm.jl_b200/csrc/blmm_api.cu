@@ -34,6 +34,7 @@ struct blmm_ctx {
   cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap the scan (host-buffer calls)
   cudaEvent_t chunk_ev[16] = {};
   cudaEvent_t copied_ev[16] = {};      // chunk's index panel has landed in h_idx
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;  // marker-side preprocessing on copy_stream
   uint8_t* h_idx = nullptr;            // pinned staging of the h2 index panel (host-buffer alt-grid calls)
   size_t h_idx_cap = 0;
   cusolverDnHandle_t solver = nullptr;
@@ -76,10 +77,11 @@ T* ws(blmm_ctx* ctx, Slot s, size_t count) {
 }
 
 // device view of an input matrix: the caller's pointer (device mode) or a staged copy (host mode)
-const double* stage_in(blmm_ctx* ctx, Slot s, const double* p, size_t count, int mem_space) {
+const double* stage_in(blmm_ctx* ctx, Slot s, const double* p, size_t count, int mem_space,
+                       cudaStream_t stream = nullptr) {
   if (mem_space == BLMM_MEM_DEVICE) return p;
   double* d = ws<double>(ctx, s, count);
-  CUDA_TRY(cudaMemcpyAsync(d, p, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(d, p, count * sizeof(double), cudaMemcpyHostToDevice, stream ? stream : ctx->stream));
   return d;
 }
 
@@ -119,10 +121,16 @@ struct Rotated {
   int n, n_pad, nq, c;
   int64_t m, p;
   const double* lambda;
+  const double* dU;  // the rotation matrix on the device (observation weights folded in)
   double *Y0, *C0, *G0;
 };
 
-Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool with_markers) {
+struct Rotated;
+void rotate_markers(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space, cudaStream_t stream);
+void rotate_traits(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space);
+
+Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool with_markers,
+                      bool with_traits = true) {
   Rotated R;
   R.n = (int)pr->n;
   R.nq = num_kchunks(pr->n);
@@ -139,23 +147,45 @@ Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool
     ctx->launches += launch_scale_rows(dU, dw, pr->n, pr->n, Uw, ctx->sm_count, ctx->stream);
     dU = Uw;
   }
+  R.dU = dU;
   R.lambda = stage_in(ctx, S_LAM, pr->lambda, n, mem_space);
   const double* dC = stage_in(ctx, S_C_IN, pr->Covar, n * R.c, mem_space);
   R.C0 = ws<double>(ctx, S_C0, (size_t)R.n_pad * R.c);
   ctx->launches += launch_rotate(dU, dC, pr->n, R.C0, R.n_pad, R.n_pad, R.n, R.c, ctx->stream);
   R.Y0 = nullptr;
-  if (R.m > 0) {
-    const double* dY = stage_in(ctx, S_Y_IN, pr->Y, n * (size_t)R.m, mem_space);
-    R.Y0 = ws<double>(ctx, S_Y0, (size_t)R.n_pad * R.m);
-    ctx->launches += launch_rotate(dU, dY, pr->n, R.Y0, R.n_pad, R.n_pad, R.n, R.m, ctx->stream);
-  }
+  if (with_traits) rotate_traits(ctx, pr, R, mem_space);
   R.G0 = nullptr;
-  if (with_markers) {
-    const double* dG = stage_in(ctx, S_G_IN, pr->G, n * (size_t)R.p, mem_space);
-    R.G0 = ws<double>(ctx, S_G0, (size_t)R.n_pad * R.p);
-    ctx->launches += launch_rotate(dU, dG, pr->n, R.G0, R.n_pad, R.n_pad, R.n, R.p, ctx->stream);
-  }
+  if (with_markers) rotate_markers(ctx, pr, R, mem_space, ctx->stream);
   return R;
+}
+
+void rotate_traits(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space) {
+  if (R.m <= 0) return;
+  const double* dY = stage_in(ctx, S_Y_IN, pr->Y, (size_t)pr->n * (size_t)R.m, mem_space);
+  R.Y0 = ws<double>(ctx, S_Y0, (size_t)R.n_pad * R.m);
+  ctx->launches += launch_rotate(R.dU, dY, pr->n, R.Y0, R.n_pad, R.n_pad, R.n, R.m, ctx->stream);
+}
+
+void rotate_markers(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space, cudaStream_t stream) {
+  const size_t n = (size_t)pr->n;
+  const double* dG = stage_in(ctx, S_G_IN, pr->G, n * (size_t)pr->p, mem_space, stream);
+  R.G0 = ws<double>(ctx, S_G0, (size_t)R.n_pad * pr->p);
+  ctx->launches += launch_rotate(R.dU, dG, pr->n, R.G0, R.n_pad, R.n_pad, R.n, pr->p, stream);
+}
+
+// The marker side of a grid scan (G -> U'G -> weight-folded marker operand) depends only on G, U and the
+// per-h2 weight constants, the trait side only on Y: the two chains are latency-bound on their own, so the
+// marker chain runs on the second stream while the main stream does the traits.  Returns after queueing;
+// the caller makes the main stream wait on ctx->join_ev before the scan.
+void fork_marker_side(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space, int nk, WeightConsts wc,
+                      bool fold_sw, double* Mop, int64_t p_pad) {
+  CUDA_TRY(cudaEventRecord(ctx->fork_ev, ctx->stream));
+  CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
+  R.p = pr->p;
+  rotate_markers(ctx, pr, R, mem_space, ctx->copy_stream);
+  ctx->launches += launch_marker_operand(R.G0, R.p, p_pad, R.n, R.n_pad, R.c, nk, wc, fold_sw, Mop, ctx->d_flags,
+                                         ctx->copy_stream);
+  CUDA_TRY(cudaEventRecord(ctx->join_ev, ctx->copy_stream));
 }
 
 WeightConsts weight_ws(blmm_ctx* ctx, int nk, int n_pad, int c) {
@@ -238,9 +268,16 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   if (m == 0) return BLMM_OK;
   reset_flags(ctx);
   const double* d_grid = upload_grid(ctx, o);
-  Rotated R = rotate_inputs(ctx, pr, ms, true);
+  // rotation matrix, covariates and weight constants first (both sides need them), then the marker side forks
+  Rotated R = rotate_inputs(ctx, pr, ms, false, false);
   WeightConsts wc = weight_ws(ctx, nk, R.n_pad, R.c);
   ctx->launches += launch_weight_consts(d_grid, nk, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags, ctx->stream);
+  const int64_t p_pad = round_up(p, SCAN_MT);
+  double* Mop = ws<double>(ctx, S_MOP, (size_t)nk * R.n_pad * p_pad);
+  ws<double>(ctx, S_G_IN, ms == BLMM_MEM_HOST ? (size_t)R.n * p : 1);  // (re)allocations before the fork: cudaFree
+  ws<double>(ctx, S_G0, (size_t)R.n_pad * p);                          // would otherwise synchronise mid-overlap
+  fork_marker_side(ctx, pr, R, ms, nk, wc, true, Mop, p_pad);
+  rotate_traits(ctx, pr, R, ms);
 
   double* Yr = ws<double>(ctx, S_YR, (size_t)R.n_pad * m);
   double* ell = ws<double>(ctx, S_ELL, (size_t)nk * m);
@@ -256,10 +293,6 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   if (!alt && h2_out) h2v = (ms == BLMM_MEM_DEVICE) ? h2_out : ws<double>(ctx, S_H2V, m);
   ctx->launches += launch_trait_stats(R.Y0, m, R.n, R.n_pad, R.c, nk, wc, lik_of(o), d_grid, Yr, ell, rss, best,
                                       ellmax, h2v, alt ? nullptr : bin_count, ctx->d_flags, ctx->stream);
-
-  const int64_t p_pad = round_up(p, SCAN_MT);
-  double* Mop = ws<double>(ctx, S_MOP, (size_t)nk * R.n_pad * p_pad);
-  ctx->launches += launch_marker_operand(R.G0, p, p_pad, R.n, R.n_pad, R.c, nk, wc, true, Mop, ctx->d_flags, ctx->stream);
 
   ScanParams P{};
   P.Mop = Mop;
@@ -310,6 +343,7 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     P.n_tiles_t = (int)(tcol_pad / SCAN_TT);
     P.nk = 1;
   }
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));  // marker operand ready
   if (ms == BLMM_MEM_HOST && alt && P.n_tiles_t >= 16 && o->chisq_df <= 0) {
     // Host-buffer alt-grid: the p x m panels (2 x 2 GB at BXD size) leave over PCIe, which takes ~5x
     // the scan itself.  Scan the trait tiles in chunks and copy each chunk's columns back on a
@@ -866,6 +900,8 @@ int blmm_create(blmm_ctx** out, int device) {
             cudaMalloc(&ctx->d_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaMallocHost(&ctx->h_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 16; ++i)
     ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->copied_ev[i], cudaEventDisableTiming) == cudaSuccess;
@@ -889,6 +925,8 @@ void blmm_destroy(blmm_ctx* ctx) {
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
   for (int i = 0; i < 16; ++i) {
     if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     if (ctx->copied_ev[i]) cudaEventDestroy(ctx->copied_ev[i]);

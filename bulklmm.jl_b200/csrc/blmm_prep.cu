@@ -5,6 +5,8 @@
 #include <float.h>
 #include <math.h>
 
+#include <algorithm>
+
 #include "blmm_kernels.cuh"
 
 namespace blmm {
@@ -337,6 +339,105 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
   }
 }
 
+// Table form of trait_stats_kernel for problems whose weight tables fit in shared memory (every BXD-size
+// grid scan).  Lane v of a warp owns one (kind a, grid point k) pair: a = 0 accumulates sum_l w_k[l] y_l^2,
+// a >= 1 accumulates t_ka = sum_l Q_ka[l] sw_k[l] y_l, in ONE pass over the trait with no cross-lane
+// reduction; then rss_k = s_k - sum_a t_ka^2 (Gram form on the trait already residualised without weights, so
+// nothing large cancels), and lane k evaluates the log-likelihood of grid point k.  The block's table
+// T[batch][l][32] (lane-contiguous: conflict-free) is built once and reused for every trait of the block.
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
+    trait_stats_table_kernel(const double* __restrict__ Y0, int64_t m, int n, int n_pad, int c, int nk, WeightConsts wc,
+                             LikParams lik, const double* __restrict__ grid_dev, double* __restrict__ Yr,
+                             double* __restrict__ ell, double* __restrict__ rss_out, int* __restrict__ best,
+                             double* __restrict__ ellmax, double* __restrict__ h2_out, int* bin_count, int* flags) {
+  extern __shared__ double smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = 32 / (1 + c);  // grid points per batch of 32 lane slots
+  const int nbatch = (nk + KB - 1) / KB;
+  double* T = smem;                                   // [nbatch][n_pad][32]
+  double* ybase = smem + (size_t)nbatch * n_pad * 32;  // [WARPS_PER_BLOCK][n_pad]
+  for (int idx = threadIdx.x; idx < nbatch * n_pad * 32; idx += blockDim.x) {
+    const int v = idx & 31, l = (idx >> 5) % n_pad, bt = (idx >> 5) / n_pad;
+    const int a = v / KB, k = bt * KB + v % KB;
+    double val = 0.0;
+    if (a <= c && k < nk && l < n) {
+      const double sw = wc.sw[(int64_t)k * n_pad + l];
+      val = (a == 0) ? wc.w[(int64_t)k * n_pad + l] : wc.Q[((int64_t)k * c + (a - 1)) * n_pad + l] * sw;
+    }
+    T[idx] = val;
+  }
+  __syncthreads();
+  const int a_lane = lane / KB, kk_lane = lane % KB;
+  double* yb = ybase + (int64_t)wid * n_pad;
+  const double* sw1 = wc.sw + (int64_t)nk * n_pad;
+  const double* Qo = wc.Q + (int64_t)nk * c * n_pad;
+  for (int64_t j = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wid; j < m; j += (int64_t)gridDim.x * WARPS_PER_BLOCK) {
+    for (int l = lane; l < n_pad; l += 32) yb[l] = Y0[j * n_pad + l];
+    __syncwarp();
+    double coef[MAXC];
+    proj_coefs(yb, sw1, Qo, n_pad, c, lane, coef);  // unweighted residual on the covariates (slot nk: w = 1)
+    for (int l = lane; l < n_pad; l += 32) {
+      const double y = proj_elem(yb, sw1, Qo, n_pad, c, l, coef);  // reads only this lane's element of yb
+      yb[l] = y;
+      Yr[j * n_pad + l] = y;
+    }
+    __syncwarp();
+    double bestv = -INFINITY;
+    int bestk = 0x7fffffff;
+    for (int bt = 0; bt < nbatch; ++bt) {
+      const double* Tb = T + (size_t)bt * n_pad * 32 + lane;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int l = 0;
+      for (; l + 4 <= n; l += 4) {
+        const double y0 = yb[l], y1 = yb[l + 1], y2 = yb[l + 2], y3 = yb[l + 3];
+        s0 = fma(Tb[(l + 0) * 32], a_lane == 0 ? y0 * y0 : y0, s0);
+        s1 = fma(Tb[(l + 1) * 32], a_lane == 0 ? y1 * y1 : y1, s1);
+        s2 = fma(Tb[(l + 2) * 32], a_lane == 0 ? y2 * y2 : y2, s2);
+        s3 = fma(Tb[(l + 3) * 32], a_lane == 0 ? y3 * y3 : y3, s3);
+      }
+      for (; l < n; ++l) {
+        const double y0 = yb[l];
+        s0 = fma(Tb[l * 32], a_lane == 0 ? y0 * y0 : y0, s0);
+      }
+      const double sv = (s0 + s1) + (s2 + s3);
+      double rss = sv;
+      const double t2 = sv * sv;
+      for (int a = 1; a <= c; ++a) rss -= __shfl_sync(0xffffffffu, t2, (a * KB + kk_lane) & 31);
+      const int k = bt * KB + kk_lane;
+      const bool valid = (a_lane == 0) && (k < nk);
+      const int kc = valid ? k : 0;
+      const double ll = null_loglik(rss, wc.slw[kc], wc.lds[kc], n, c, lik, nullptr);
+      if (valid) {
+        ell[(int64_t)k + j * nk] = ll;
+        rss_out[(int64_t)k * m + j] = rss;
+        if (!(sqrt(rss) > DBL_EPSILON)) atomicExch(&flags[FLAG_ZERO_NORM], 1);
+        if (ll > bestv) {  // within a lane k only grows, so strict > keeps the first maximum
+          bestv = ll;
+          bestk = k;
+        }
+      }
+    }
+    // first maximum over the grid (findmax): larger value wins, equal values -> smaller k
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
+      if (ov > bestv || (ov == bestv && ok < bestk)) {
+        bestv = ov;
+        bestk = ok;
+      }
+    }
+    if (lane == 0) {
+      if (bestk == 0x7fffffff) bestk = 0;  // every log-likelihood NaN: as findmax on NaNs, first index
+      best[j] = bestk;
+      ellmax[j] = bestv;
+      if (h2_out) h2_out[j] = grid_dev[bestk];
+      if (bin_count) atomicAdd(&bin_count[bestk], 1);
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
     marker_operand_kernel(const double* __restrict__ G0, int64_t p, int64_t p_pad, int n, int n_pad, int c, int nk,
                           WeightConsts wc, int fold_sw, double* __restrict__ Mop, int* flags) {
@@ -503,6 +604,22 @@ int launch_trait_stats(const double* Y0, int64_t m, int n, int n_pad, int c, int
                        LikParams lik, const double* grid_dev, double* Yr, double* ell, double* rss,
                        int* best, double* ellmax, double* h2_out, int* bin_count, int* flags,
                        cudaStream_t stream) {
+  // table form when the block's weight table fits in shared memory (BXD-size grid scans: 20 KB)
+  const int KB = 32 / (1 + c);
+  const int nbatch = (nk + KB - 1) / KB;
+  const size_t table_smem = ((size_t)nbatch * n_pad * 32 + (size_t)WARPS_PER_BLOCK * n_pad) * sizeof(double);
+  if (table_smem <= 96 * 1024) {
+    if (table_smem > 48 * 1024)
+      cudaFuncSetAttribute(trait_stats_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_smem);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const unsigned blocks = (unsigned)std::min<int64_t>(want, (int64_t)sms * 4);  // one resident wave
+    trait_stats_table_kernel<<<blocks, 32 * WARPS_PER_BLOCK, table_smem, stream>>>(
+        Y0, m, n, n_pad, c, nk, wc, lik, grid_dev, Yr, ell, rss, best, ellmax, h2_out, bin_count, flags);
+    return 1;
+  }
   const size_t smem = (size_t)WARPS_PER_BLOCK * n_pad * sizeof(double);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(trait_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
