@@ -33,10 +33,19 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
   for (int i = 0; i < NT; ++i) S[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < C; ++i) t[i] = 0.0;
-  double yy = 0.0, slw = 0.0;
+  // sum_l log w_l = -log prod_l (delta lambda_l + 1): one logarithm per lane instead of one per element (the
+  // running product is folded into the sum every 8 factors; a factor is at most ~2^40 for h2 <= 1 - 1e-8)
+  double yy = 0.0, slw = 0.0, prod = 1.0;
+  int since = 0;
   for (int l = d.lane; l < d.n; l += 32) {
-    const double w = 1.0 / (delta * d.lambda[l] + 1.0);
-    slw += log(w);
+    const double dl = fma(delta, d.lambda[l], 1.0);
+    const double w = 1.0 / dl;
+    prod *= dl;
+    if (++since == 8) {
+      slw -= log(prod);
+      prod = 1.0;
+      since = 0;
+    }
     const double y = d.y[l];
     const double wy = w * y;
     yy = fma(wy, y, yy);
@@ -55,6 +64,7 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
       }
     }
   }
+  slw -= log(prod);
   yy = warp_sum(yy);
   slw = warp_sum(slw);
 #pragma unroll
@@ -62,7 +72,7 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
 #pragma unroll
   for (int i = 0; i < C; ++i) t[i] = warp_sum(t[i]);
   // Cholesky S = L L' (packed lower, row-major), forward solve L u = t
-  double lds = 0.0, uu = 0.0;
+  double uu = 0.0;
   double Lm[NT], u[C];
 #pragma unroll
   for (int a = 0; a < C; ++a) {
@@ -78,41 +88,38 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
     for (int k = 0; k < a; ++k) s -= Lm[a * (a + 1) / 2 + k] * u[k];
     u[a] = s / Lm[a * (a + 1) / 2 + a];
     uu = fma(u[a], u[a], uu);
-    lds += log(Lm[a * (a + 1) / 2 + a]);
   }
-  lds *= 2.0;
   const double rss = yy - uu;
   const double a = d.lik.prior_a, b = d.lik.prior_b;
   const double pdf = (b > 0.0) ? b + 2.0 : b;
   const double ab = a * b;
   const double denom = d.lik.reml ? ((double)(d.n - C) + pdf) : ((double)d.n + pdf);
   const double sigma2 = (rss + ab) / denom;
-  double ll = -0.5 * (((double)d.n + b) * log(sigma2) - slw + (rss + ab) / sigma2);
-  if (d.lik.reml) ll += 0.5 * ((double)C * log(sigma2) - lds);
+  // log sigma2 and the log of the C Cholesky diagonals in ONE evaluation: lane 0 takes sigma2, lane a+1 L_aa
+  double arg = sigma2;
+#pragma unroll
+  for (int i = 0; i < C; ++i)
+    if (d.lane == i + 1) arg = Lm[i * (i + 1) / 2 + i];
+  const double lg = log(arg);
+  const double log_s2 = __shfl_sync(0xffffffffu, lg, 0);
+  double lds = 0.0;
+#pragma unroll
+  for (int i = 0; i < C; ++i) lds += __shfl_sync(0xffffffffu, lg, i + 1);
+  lds *= 2.0;
+  double ll = -0.5 * (((double)d.n + b) * log_s2 - slw + (rss + ab) / sigma2);
+  if (d.lik.reml) ll += 0.5 * ((double)C * log_s2 - lds);
   if (sigma2_out) *sigma2_out = sigma2;
   return -ll;
 }
 
-__device__ double neg_loglik(const FitData& d, double h2, double* sigma2_out) {
-  switch (d.c) {
-    case 1: return neg_loglik_c<1>(d, h2, sigma2_out);
-    case 2: return neg_loglik_c<2>(d, h2, sigma2_out);
-    case 3: return neg_loglik_c<3>(d, h2, sigma2_out);
-    case 4: return neg_loglik_c<4>(d, h2, sigma2_out);
-    case 5: return neg_loglik_c<5>(d, h2, sigma2_out);
-    case 6: return neg_loglik_c<6>(d, h2, sigma2_out);
-    case 7: return neg_loglik_c<7>(d, h2, sigma2_out);
-    default: return neg_loglik_c<8>(d, h2, sigma2_out);
-  }
-}
-
 // Optim.jl `optimize(f, lo, hi, Brent())` with its defaults rel_tol = sqrt(eps), abs_tol = eps,
 // iterations = 1000 (call site src/gridbrent.jl:16).
+template <int C>
 __device__ void brent(const FitData& d, double lo, double hi, double* xmin, double* fmin_out) {
   const double golden = 0.5 * (3.0 - sqrt(5.0));
   const double rel_tol = sqrt(DBL_EPSILON), abs_tol = DBL_EPSILON;
   double x = lo + golden * (hi - lo);
-  double fx = neg_loglik(d, x, nullptr);
+  double fx = neg_loglik_c<C>(d, x, nullptr);
   double step = 0.0, old_step = 0.0;
   double xo = x, xoo = x, fo = fx, foo = fx;
   for (int it = 0; it < 1000; ++it) {
@@ -140,7 +147,7 @@ __device__ void brent(const FitData& d, double lo, double hi, double* xmin, doub
       step = golden * old_step;
     }
     const double xn = (fabs(step) >= tol) ? x + step : x + ((step > 0.0) ? tol : -tol);
-    const double fn = neg_loglik(d, xn, nullptr);
+    const double fn = neg_loglik_c<C>(d, xn, nullptr);
     if (fn < fx) {
       if (xn < x)
         hi = x;
@@ -166,7 +173,10 @@ __device__ void brent(const FitData& d, double lo, double hi, double* xmin, doub
   *fmin_out = fx;
 }
 
-__global__ void __launch_bounds__(32 * FIT_WARPS)
+// Templated on the covariate count so that the common c = 1..3 cases keep their Gram matrices in a few
+// registers (a run-time switch over all eight sizes cost 200 registers per thread: 8 warps per SM).
+template <int C>
+__global__ void __launch_bounds__(32 * FIT_WARPS, C <= 2 ? 8 : (C <= 4 ? 4 : 2))
     fit_h2_kernel(const double* __restrict__ Yr, int64_t m, int n, int n_pad, int c, const double* __restrict__ C0,
                   const double* __restrict__ lambda, LikParams lik, int optim_interval, double* __restrict__ h2_out,
                   double* __restrict__ sigma2_out, double* __restrict__ ell_out) {
@@ -180,14 +190,14 @@ __global__ void __launch_bounds__(32 * FIT_WARPS)
     const double lo = (double)i / (double)optim_interval;
     const double hi = (i + 1 == optim_interval) ? 1.0 : (double)(i + 1) / (double)optim_interval;
     double x, f;
-    brent(d, lo, hi, &x, &f);
+    brent<C>(d, lo, hi, &x, &f);
     if (i == 0 || f < bf) {
       bx = x;
       bf = f;
     }
   }
   double s2;
-  const double f = neg_loglik(d, bx, &s2);
+  const double f = neg_loglik_c<C>(d, bx, &s2);
   if (lane == 0) {
     if (h2_out) h2_out[j] = bx;
     if (sigma2_out) sigma2_out[j] = s2;
@@ -202,8 +212,16 @@ int launch_fit_h2(const double* Yr, int64_t m, int n, int n_pad, int c, const do
                   double* ell, int* flags, cudaStream_t stream) {
   (void)flags;
   const unsigned blocks = (unsigned)((m + FIT_WARPS - 1) / FIT_WARPS);
-  fit_h2_kernel<<<blocks, 32 * FIT_WARPS, 0, stream>>>(Yr, m, n, n_pad, c, C0, lambda, lik, optim_interval, h2,
-                                                       sigma2, ell);
+#define BLMM_FIT(CC)                                                                                          \
+  case CC:                                                                                                    \
+    fit_h2_kernel<CC><<<blocks, 32 * FIT_WARPS, 0, stream>>>(Yr, m, n, n_pad, c, C0, lambda, lik, optim_interval, h2, \
+                                                             sigma2, ell);                                    \
+    break;
+  switch (c) {
+    BLMM_FIT(1) BLMM_FIT(2) BLMM_FIT(3) BLMM_FIT(4) BLMM_FIT(5) BLMM_FIT(6) BLMM_FIT(7) BLMM_FIT(8)
+    default: return 0;
+  }
+#undef BLMM_FIT
   return 1;
 }
 
