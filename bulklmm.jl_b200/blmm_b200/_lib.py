@@ -58,6 +58,8 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "blmm_scan_null": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.POINTER(Opts), C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "blmm_scan_alt": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.POINTER(Opts), C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
     "blmm_lod2log10p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                   C.c_void_p, C.c_int]),
     "blmm_thresholds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),

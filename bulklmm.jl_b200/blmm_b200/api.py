@@ -262,6 +262,20 @@ class Engine:
         self._check(self.lib.blmm_scan_null(self.h, C.byref(pr), C.byref(o), _ptr(lod), _ptr(s2), _ptr(h2)))
         return lod, s2, h2
 
+    def scan_alt_host(self, y, G, Covar, U, lam, reml=False, prior_variance=0.0, prior_sample_size=0.0,
+                      optim_interval=1, weights=None):
+        """blmm_scan_alt: per-marker variance components (src/scan.jl:397-453)."""
+        y, G, Covar, U = _f(y), _f(G), _f(Covar), _f(U)
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        weights = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+        p = G.shape[1]
+        pr = self._host_problem(y, G, Covar, U, lam, weights)
+        o, _ = self.make_opts(method=L.METHOD_NULL_EXACT, reml=reml, prior_variance=prior_variance,
+                              prior_sample_size=prior_sample_size, optim_interval=optim_interval)
+        lod, h2e, s2, h2 = np.empty(p), np.empty(p), np.empty(1), np.empty(1)
+        self._check(self.lib.blmm_scan_alt(self.h, C.byref(pr), C.byref(o), _ptr(lod), _ptr(h2e), _ptr(s2), _ptr(h2)))
+        return lod, h2e, float(s2[0]), float(h2[0])
+
     def scan_perms_host(self, y, G, Covar, U, lam, perm_idx, reml=False, prior_variance=0.0,
                         prior_sample_size=0.0, optim_interval=1, want_L=True, want_max=True, weights=None):
         y, G, Covar, U = _f(y), _f(G), _f(Covar), _f(U)
@@ -409,12 +423,24 @@ def scan(y, g, K, covar=None, weights=None, prior_variance: float = 0.0, prior_s
         y = y.reshape(-1, 1)
     if covar is None and not addIntercept:
         raise BlmmError(L.E_INVALID, "Intercept has to be added when no other covariate is given.")
-    if assumption != "null":
+    if assumption not in ("null", "alt"):
         raise BlmmError(L.E_INVALID, "Assumption keyword is not supported. Please enter null or alt.")
+    if assumption == "alt" and permutation_test:
+        raise BlmmError(L.E_INVALID, "Permutation test option currently is not supported for the alternative assumption.")
     if y.shape[1] != 1:
         raise BlmmError(L.E_ONE_TRAIT, "Can only handle one trait.")
     y, g, C0, K, weights = _prep(y, g, covar, K, weights, addIntercept, eng)
     n = y.shape[0]
+    if assumption == "alt":
+        # scan_alt, src/scan.jl:397-453
+        if decomposition is None:
+            U, lam, _ = eng.decompose(K, decomp_scheme)
+        else:
+            U, lam = decomposition
+        lod, h2e, s2, h2 = eng.scan_alt_host(y, g, C0, U, lam, reml=reml, prior_variance=prior_variance,
+                                             prior_sample_size=prior_sample_size, optim_interval=optim_interval,
+                                             weights=weights)
+        return SimpleNamespace(sigma2_e=s2, h2_null=h2, h2_each_marker=h2e, lod=lod)
     if not permutation_test:
         # scan_null, src/scan.jl:310-360
         if decomposition is None:

@@ -596,6 +596,43 @@ int bulkscan_exact(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, do
   return BLMM_OK;
 }
 
+// scan(...; assumption = "alt"), src/scan.jl:397-453: one trait, variance components re-estimated per marker
+int scan_alt(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, double* lod_out, double* h2_each_out,
+             double* sigma2_out, double* h2_out) {
+  if (pr && pr->m != 1) throw Fail{BLMM_E_ONE_TRAIT, "Can only handle one trait."};
+  check_problem(pr, true);
+  if (!lod_out) throw Fail{BLMM_E_INVALID, "lod_out is NULL"};
+  if (o->optim_interval < 1) throw Fail{BLMM_E_INVALID, "optim_interval must be >= 1"};
+  if (pr->c + 1 > MAXC) throw Fail{BLMM_E_INVALID, "scan_alt supports at most " + std::to_string(MAXC - 1) + " covariates"};
+  const int ms = o->mem_space;
+  const bool dev = ms == BLMM_MEM_DEVICE;
+  const int64_t p = pr->p;
+  reset_flags(ctx);
+  Rotated R = rotate_inputs(ctx, pr, ms, true);
+  double* Yr = residualised_traits(ctx, R, o);
+  double* misc = ws<double>(ctx, S_MISC, 8);  // [0] h2_null, [1] sigma2, [2] ell_null
+  ctx->launches += launch_fit_h2(Yr, 1, R.n, R.n_pad, R.c, R.C0, R.lambda, lik_of(o), o->optim_interval, misc, misc + 1,
+                                 nullptr, ctx->d_flags, ctx->stream);
+  double* dlod = dev ? lod_out : ws<double>(ctx, S_L, p);
+  double* dh2 = h2_each_out ? (dev ? h2_each_out : ws<double>(ctx, S_H2P, p)) : nullptr;
+  const int launched = launch_scan_alt(Yr, R.G0, p, R.n, R.n_pad, R.c, R.C0, R.lambda, lik_of(o), o->optim_interval,
+                                       misc, misc + 2, dlod, dh2, ctx->stream);
+  if (!launched) throw Fail{BLMM_E_INVALID, "unsupported covariate count"};
+  ctx->launches += launched;
+  CUDA_TRY(cudaGetLastError());
+  if (dev) {
+    if (h2_out) CUDA_TRY(cudaMemcpyAsync(h2_out, misc, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (sigma2_out) CUDA_TRY(cudaMemcpyAsync(sigma2_out, misc + 1, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    copy_out(ctx, lod_out, dlod, p, ms);
+    if (h2_each_out) copy_out(ctx, h2_each_out, dh2, p, ms);
+    if (h2_out) copy_out(ctx, h2_out, misc, 1, ms);
+    if (sigma2_out) copy_out(ctx, sigma2_out, misc + 1, 1, ms);
+    finish_and_check(ctx);
+  }
+  return BLMM_OK;
+}
+
 int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const int32_t* perm_idx, int64_t nperms,
                double* lod_out, double* Lperms_out, double* maxlod_out, double* sigma2_out, double* h2_out) {
   if (pr && pr->m != 1) throw Fail{BLMM_E_ONE_TRAIT, "Can only handle one trait."};
@@ -1021,6 +1058,14 @@ int blmm_scan_null(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opt
   return guarded(ctx, [&] {
     if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
     return bulkscan_exact(ctx, prob, opts, lod_out, h2_out, sigma2_out);
+  });
+}
+
+int blmm_scan_alt(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* lod_out,
+                  double* h2_each_marker_out, double* sigma2_out, double* h2_out) {
+  return guarded(ctx, [&] {
+    if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
+    return scan_alt(ctx, prob, opts, lod_out, h2_each_marker_out, sigma2_out, h2_out);
   });
 }
 

@@ -20,6 +20,8 @@ struct FitData {
   const double* lambda;  // [n]
   int n, n_pad, c, lane;
   LikParams lik;
+  const double* xcol;    // scan_alt: the marker column that takes the LAST covariate slot (else nullptr)
+  bool sqrt_weights;     // scan_alt's final likelihoods: wls is handed sqrt(w) as its weights (src/scan.jl:440-441)
 };
 
 // -ell(h2) and sigma2.  The covariate projection uses the Gram form S = C'WC, t = C'Wy,
@@ -39,7 +41,7 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
   int since = 0;
   for (int l = d.lane; l < d.n; l += 32) {
     const double dl = fma(delta, d.lambda[l], 1.0);
-    const double w = 1.0 / dl;
+    const double w = d.sqrt_weights ? 1.0 / sqrt(dl) : 1.0 / dl;
     prod *= dl;
     if (++since == 8) {
       slw -= log(prod);
@@ -51,7 +53,7 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
     yy = fma(wy, y, yy);
     double cv[C];
 #pragma unroll
-    for (int a = 0; a < C; ++a) cv[a] = d.C0[(int64_t)a * d.n_pad + l];
+    for (int a = 0; a < C; ++a) cv[a] = (a == C - 1 && d.xcol) ? d.xcol[l] : d.C0[(int64_t)a * d.n_pad + l];
     int idx = 0;
 #pragma unroll
     for (int a = 0; a < C; ++a) {
@@ -65,6 +67,7 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
     }
   }
   slw -= log(prod);
+  if (d.sqrt_weights) slw *= 0.5;
   yy = warp_sum(yy);
   slw = warp_sum(slw);
 #pragma unroll
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(32 * FIT_WARPS, C <= 2 ? 8 : (C <= 4 ? 4 : 2))
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t j = (int64_t)blockIdx.x * FIT_WARPS + wid;
   if (j >= m) return;
-  FitData d{Yr + j * n_pad, C0, lambda, n, n_pad, c, lane, lik};
+  FitData d{Yr + j * n_pad, C0, lambda, n, n_pad, c, lane, lik, nullptr, false};
   // gridbrent: points = range(0, 1, length = optim_interval + 1); keep the first of equal minima
   double bx = 0.0, bf = INFINITY;
   for (int i = 0; i < optim_interval; ++i) {
@@ -205,7 +208,77 @@ __global__ void __launch_bounds__(32 * FIT_WARPS, C <= 2 ? 8 : (C <= 4 ? 4 : 2))
   }
 }
 
+// gridbrent over [0, 1] in optim_interval pieces (src/gridbrent.jl:9-24): first of equal minima
+template <int C>
+__device__ double fit_one(const FitData& d, int optim_interval) {
+  double bx = 0.0, bf = INFINITY;
+  for (int i = 0; i < optim_interval; ++i) {
+    const double lo = (double)i / (double)optim_interval;
+    const double hi = (i + 1 == optim_interval) ? 1.0 : (double)(i + 1) / (double)optim_interval;
+    double x, f;
+    brent<C>(d, lo, hi, &x, &f);
+    if (i == 0 || f < bf) {
+      bx = x;
+      bf = f;
+    }
+  }
+  return bx;
+}
+
+// scan_alt (src/scan.jl:397-453), one warp per marker: covariates [C0 g_i] (C = c + 1 columns), the variance
+// components re-estimated by Brent for every marker, then lod_i = (ell_alt - ell_null) / ln 10 with both
+// likelihoods evaluated as the reference does — ML, and with sqrt(w) passed to wls as the weights.
+// ell_null comes from scan_alt_null_kernel.
+template <int C>
+__global__ void __launch_bounds__(32 * FIT_WARPS, C <= 2 ? 8 : (C <= 4 ? 4 : 2))
+    scan_alt_kernel(const double* __restrict__ y, const double* __restrict__ G0, int64_t p, int n, int n_pad,
+                    const double* __restrict__ C0, const double* __restrict__ lambda, LikParams lik,
+                    int optim_interval, const double* __restrict__ ell_null, double* __restrict__ lod,
+                    double* __restrict__ h2_each) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * FIT_WARPS + wid;
+  if (i >= p) return;
+  FitData d{y, C0, lambda, n, n_pad, C, lane, lik, G0 + i * n_pad, false};
+  const double h2 = fit_one<C>(d, optim_interval);
+  d.sqrt_weights = true;
+  d.lik.reml = 0;
+  const double ell_alt = -neg_loglik_c<C>(d, h2, nullptr);
+  if (lane == 0) {
+    lod[i] = (ell_alt - ell_null[0]) / 2.30258509299404568402;
+    if (h2_each) h2_each[i] = h2;
+  }
+}
+
+// ell_null of scan_alt: wls(y0, X0_covar, sqrt(w(h2_null)), prior).ell, one warp
+template <int C>
+__global__ void scan_alt_null_kernel(const double* __restrict__ y, int n, int n_pad, const double* __restrict__ C0,
+                                     const double* __restrict__ lambda, LikParams lik,
+                                     const double* __restrict__ h2_null, double* __restrict__ ell_null) {
+  lik.reml = 0;
+  FitData d{y, C0, lambda, n, n_pad, C, (int)(threadIdx.x & 31), lik, nullptr, true};
+  const double e = -neg_loglik_c<C>(d, h2_null[0], nullptr);
+  if (threadIdx.x == 0) ell_null[0] = e;
+}
+
 }  // namespace
+
+int launch_scan_alt(const double* y, const double* G0, int64_t p, int n, int n_pad, int c, const double* C0,
+                    const double* lambda, LikParams lik, int optim_interval, const double* h2_null, double* ell_null,
+                    double* lod, double* h2_each, cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((p + FIT_WARPS - 1) / FIT_WARPS);
+#define BLMM_ALT(CC)                                                                                              \
+  case CC:                                                                                                        \
+    scan_alt_null_kernel<CC><<<1, 32, 0, stream>>>(y, n, n_pad, C0, lambda, lik, h2_null, ell_null);              \
+    scan_alt_kernel<CC + 1><<<blocks, 32 * FIT_WARPS, 0, stream>>>(y, G0, p, n, n_pad, C0, lambda, lik,           \
+                                                                   optim_interval, ell_null, lod, h2_each);       \
+    break;
+  switch (c) {
+    BLMM_ALT(1) BLMM_ALT(2) BLMM_ALT(3) BLMM_ALT(4) BLMM_ALT(5) BLMM_ALT(6) BLMM_ALT(7)
+    default: return 0;
+  }
+#undef BLMM_ALT
+  return 2;
+}
 
 int launch_fit_h2(const double* Yr, int64_t m, int n, int n_pad, int c, const double* C0,
                   const double* lambda, LikParams lik, int optim_interval, double* h2, double* sigma2,

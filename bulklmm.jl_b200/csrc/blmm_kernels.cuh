@@ -98,6 +98,13 @@ int launch_fit_h2(const double* Yr, int64_t m, int n, int n_pad, int c, const do
                   const double* lambda, LikParams lik, int optim_interval, double* h2, double* sigma2,
                   double* ell, int* flags, cudaStream_t stream);
 
+// scan_alt (src/scan.jl:397-453) for ONE trait y (residualised, padded): per-marker Brent with covariates
+// [C0 g_i] (c + 1 <= MAXC columns), lod_i = (ell_alt_i - ell_null) / ln 10, h2_each[i] (nullable).
+// h2_null: device scalar from launch_fit_h2; ell_null: device scalar workspace.
+int launch_scan_alt(const double* y, const double* G0, int64_t p, int n, int n_pad, int c, const double* C0,
+                    const double* lambda, LikParams lik, int optim_interval, const double* h2_null, double* ell_null,
+                    double* lod, double* h2_each, cudaStream_t stream);
+
 // ---- the fused scan (blmm_scan.cu) ------------------------------------------------------------
 // For every (marker i, packed trait column s):
 //     d_k = sum_l Mop[k][i][l] * Top[s][l]

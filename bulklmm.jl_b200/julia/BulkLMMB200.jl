@@ -237,11 +237,24 @@ function scan(y::Array{Float64, 2}, g::Array{Float64, 2}, covar::Array{Float64, 
               assumption::String = "null", method::String = "qr", optim_interval::Int64 = 1,
               permutation_test::Bool = false, nperms::Int64 = 1024, rndseed::Int64 = 0,
               decomp_scheme::String = "eigen", ctx::Context = default_context())
-    assumption == "null" || throw(error("Assumption keyword is not supported. Please enter null or alt."))
+    assumption in ("null", "alt") || throw(error("Assumption keyword is not supported. Please enter null or alt."))
+    (assumption == "alt" && permutation_test) &&
+        throw(error("Permutation test option currently is not supported for the alternative assumption."))
     size(y, 2) == 1 || throw(error("Can only handle one trait."))
     ys, gs, cs, Ks, w = prep(y, g, covar, K, weights, addIntercept; ctx = ctx)
     (n, p) = size(gs)
     U, lambda = decompose(Ks; decomp_scheme = decomp_scheme, ctx = ctx)
+    if assumption == "alt"      # scan_alt, src/scan.jl:397-453: variance components re-estimated per marker
+        lod = Array{Float64, 1}(undef, p); h2e = Array{Float64, 1}(undef, p)
+        s2 = Ref{Float64}(0.0); h2 = Ref{Float64}(0.0)
+        prob = BlmmProblem(n, p, 1, size(cs, 2), pointer(ys), pointer(gs), pointer(cs), pointer(U), pointer(lambda), wptr(w))
+        opts = BlmmOpts(METHOD_NULL_EXACT, reml, prior_variance, prior_sample_size, C_NULL, 0, optim_interval,
+                        H2PANEL_REFERENCE, BLMM_MEM_HOST, 0)
+        GC.@preserve ys gs cs U lambda w lod h2e check(ctx, ccall((:blmm_scan_alt, libblmm), Cint,
+            (Ptr{Cvoid}, Ref{BlmmProblem}, Ref{BlmmOpts}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Float64}),
+            ctx.handle, prob, opts, lod, h2e, s2, h2))
+        return (sigma2_e = s2[], h2_null = h2[], h2_each_marker = h2e, lod = lod)
+    end
     if !permutation_test        # scan_null, src/scan.jl:310-360
         lod = Array{Float64, 2}(undef, p, 1); s2 = Ref{Float64}(0.0); h2 = Ref{Float64}(0.0)
         prob = BlmmProblem(n, p, 1, size(cs, 2), pointer(ys), pointer(gs), pointer(cs), pointer(U), pointer(lambda), wptr(w))

@@ -176,6 +176,14 @@ BLMM_API int blmm_scan_perms(blmm_ctx* ctx, const blmm_problem* prob, const blmm
 BLMM_API int blmm_scan_null(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* lod_out,
                    double* sigma2_out, double* h2_out);
 
+/* scan(y, g, covar, K; assumption = "alt"), src/scan.jl:397-453, prob->m == 1: the variance components are
+ * re-estimated by Brent for every marker (covariates [Covar g_i], so c + 1 <= 8), and
+ * lod_i = (ell_alt_i - ell_null) / ln 10 with both likelihoods evaluated exactly as the reference does (ML, and
+ * with sqrt(w) handed to wls as the weights, src/scan.jl:436-442).  lod_out: p; h2_each_marker_out: p or NULL;
+ * sigma2_out, h2_out: the null fit, one value each or NULL.                                          */
+BLMM_API int blmm_scan_alt(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* lod_out,
+                  double* h2_each_marker_out, double* sigma2_out, double* h2_out);
+
 /* ---- post-processing ------------------------------------------------------------------------ */
 /* lod2log10p.(L, df), src/util.jl:199-206: out = -logccdf(Chisq(df), 2 ln10 lod) / ln10, elementwise over a
  * rows x cols matrix (ld_in / ld_out leading dimensions, 0 => rows).  out may alias lod.            */

@@ -653,6 +653,31 @@ def scan_null(y, g, covar, K, prior, addIntercept, reml=False, method="qr", opti
     return {"sigma2_e": out00.sigma2, "h2_null": out00.h2, "lod": lod}
 
 
+def scan_alt(y, g, covar, K, prior, addIntercept, reml=False, method="qr", optim_interval=1,
+             decomp_scheme="eigen", Ut=None, lam=None):
+    """src/scan.jl:397-453 — variance components re-estimated for every marker.  As in the reference the two
+    final likelihoods are `wls(..., sqrtw, prior)`: the SQUARE ROOTS of the weights are handed to wls as its
+    weights, and reml is left at wls's default (false) whatever `reml` was used for the fits."""
+    n, p = g.shape
+    c = covar.shape[1] + (1 if addIntercept else 0)
+    y0, X0, lam0 = transform_rotation(y, np.hstack([covar, g]), K, addIntercept=addIntercept,
+                                      decomp_scheme=decomp_scheme, Ut=Ut, lam=lam)
+    X0_cov = X0[:, :c]
+    out00 = fitlmm(y0, X0_cov, lam0, prior, reml=reml, method=method, optim_interval=optim_interval)
+    sqrtw_null = np.sqrt(make_weights(out00.h2, lam0))
+    ell_null = wls(y0, X0_cov, sqrtw_null, prior).ell
+    lod = np.zeros(p)
+    pve = np.zeros(p)
+    X = X0[:, :c + 1].copy()
+    for i in range(p):
+        X[:, c] = X0[:, c + i]
+        out11 = fitlmm(y0, X, lam0, prior, reml=reml, method=method, optim_interval=optim_interval)
+        sqrtw_alt = np.sqrt(make_weights(out11.h2, lam0))
+        lod[i] = (wls(y0, X, sqrtw_alt, prior).ell - ell_null) / math.log(10.0)
+        pve[i] = out11.h2
+    return {"sigma2_e": out00.sigma2, "h2_null": out00.h2, "h2_each_marker": pve, "lod": lod}
+
+
 def scan_perms_lite(y, g, covar, K, perm_idx, prior_variance=1.0, prior_sample_size=0.0,
                     addIntercept=True, method="qr", optim_interval=1, reml=False,
                     decomp_scheme="eigen", Ut=None, lam=None):
@@ -677,7 +702,7 @@ def scan(y, g, K, covar=None, weights=None, prior_variance=0.0, prior_sample_siz
          addIntercept=True, reml=False, assumption="null", method="qr", optim_interval=1,
          permutation_test=False, nperms=1024, rndseed=0, perm_idx=None, decomp_scheme="eigen",
          Ut=None, lam=None):
-    """src/scan.jl:94-271 (the null-assumption branches; `assumption="alt"` is out of scope)."""
+    """src/scan.jl:94-271."""
     y = np.asarray(y, dtype=np.float64)
     if y.ndim == 1:
         y = y.reshape(-1, 1)
@@ -694,6 +719,11 @@ def scan(y, g, K, covar=None, weights=None, prior_variance=0.0, prior_sample_siz
         covar = W[:, None] * (np.hstack([np.ones((n, 1)), covar]) if addIntercept else covar)
         K = W[:, None] * K * W[None, :]
         addIntercept = False
+    if assumption == "alt":
+        if permutation_test:
+            raise OracleError("Permutation test option currently is not supported for the alternative assumption.")
+        return scan_alt(y, g, covar, K, [prior_variance, prior_sample_size], addIntercept, reml=reml,
+                        method=method, optim_interval=optim_interval, decomp_scheme=decomp_scheme, Ut=Ut, lam=lam)
     if assumption != "null":
         raise OracleError("Assumption keyword is not supported. Please enter null or alt.")
     if permutation_test:

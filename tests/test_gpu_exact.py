@@ -142,3 +142,24 @@ def test_scan_perms_nonzero_h2(engine):
         if hits == 3:
             break
     assert hits >= 2, "synthetic traits did not produce interior h2 estimates"
+
+
+@pytest.mark.parametrize("reml,ncov", [(False, 0), (True, 0), (False, 2)])
+def test_scan_alt_per_marker_variance_components(engine, reml, ncov):
+    """scan(...; assumption="alt") (src/scan.jl:397-453): Brent per marker on the device against the oracle's
+    restatement, including the reference's sqrt-weights final likelihoods.  h2 within the Brent tolerance; LODs
+    to the sensitivity that tolerance allows (the objective is flat at its optimum)."""
+    from blmm_b200 import scan
+    Y, G, K = synth.make_problem(79, 48, 4, seed_g=61, seed_y=62)
+    Ut, lam = orc.decompose(K)
+    dec = (np.asfortranarray(Ut.T), lam)
+    Cv = synth.make_covar(79)[:, :ncov] if ncov else None
+    y = Y[:, 1]
+    kw = dict(prior_variance=float(np.var(y, ddof=1)), prior_sample_size=0.1, reml=reml)
+    r = scan(y, G, K, covar=Cv, assumption="alt", decomposition=dec, engine=engine, **kw)
+    ref = orc.scan(y, G, K, covar=Cv, assumption="alt", Ut=Ut, lam=lam, **kw)
+    assert abs(r.h2_null - ref["h2_null"]) < 1e-6 and abs(r.sigma2_e - ref["sigma2_e"]) < 1e-6 * max(1.0, ref["sigma2_e"])
+    assert np.max(np.abs(r.h2_each_marker - ref["h2_each_marker"])) < 2e-6
+    assert np.max(np.abs(r.lod - ref["lod"]) / np.maximum(1.0, np.abs(ref["lod"]))) < 1e-6
+    with pytest.raises(Exception, match="Permutation test option currently is not supported"):
+        scan(y, G, K, assumption="alt", permutation_test=True, engine=engine)
