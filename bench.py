@@ -253,6 +253,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # host threads that expand the h2 index panel in host-buffer calls: the ranks of one box share its cores
+    os.environ.setdefault("BLMM_B200_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 2) // world - 1))))
     if world > 1:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -357,9 +359,12 @@ def main():
             hopts, keep2 = eng.make_opts(method=self.method, mem_space=L.MEM_HOST, **w["opts"])
             self.call(hpr, hopts, pout, pperm)  # warm (allocates staging)
             barrier()
+            per = []
             t0 = time.perf_counter()
             for _ in range(steps):
+                t1 = time.perf_counter()
                 self.call(hpr, hopts, pout, pperm)  # blocking: returns with results on the host
+                per.append((time.perf_counter() - t1) * 1e3)
             barrier()
             dt = time.perf_counter() - t0
             if world > 1:
@@ -374,7 +379,7 @@ def main():
             pcie_d2h = d2h - (pout[1].numel() * 7 if self.w["method"] == "alt-grid" else 0)
             return {"value": self.tests_total * steps / dt, "unit": "tests/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(pcie_d2h), "host_output_bytes_per_step": int(d2h),
-                    "ms_per_step": dt / steps * 1e3, "steps": steps,
+                    "ms_per_step": dt / steps * 1e3, "ms_each_step": [round(x, 2) for x in per], "steps": steps,
                     "note": "per rank bytes; pinned host buffers; wall clock around blocking C-ABI calls; the "
                             "alt-grid copy-back overlaps the scan (trait-tile chunks on a second stream); the h2 panel crosses "
                             "PCIe as one-byte grid indices and is expanded to Float64 by host threads inside the call "

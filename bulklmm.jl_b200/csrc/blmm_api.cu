@@ -352,7 +352,12 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     // expanded to grid[index] in the caller's Float64 array by host threads while later chunks copy.
     const int nchunk = 8;
     const int n_tiles = P.n_tiles_t;
-    const bool idx_panel = dH && P.nq <= scan_max_nq(P.nk);
+    // Worth it when the panel is large (PCIe time saved > host expansion time): >= 1e8 entries by default.
+    // BLMM_B200_H2_TRANSFER = index | f64 overrides; BLMM_B200_HOST_THREADS sets the expansion thread count
+    // (default min(16, cores - 1); several ranks sharing one host should divide the cores between them).
+    const char* h2_mode = getenv("BLMM_B200_H2_TRANSFER");
+    const bool want_idx = h2_mode ? (h2_mode[0] == 'i') : ((double)p * (double)m >= 1e8);
+    const bool idx_panel = dH && want_idx && P.nq <= scan_max_nq(P.nk);
     uint8_t* dI = nullptr;
     if (idx_panel) {
       dI = ws<uint8_t>(ctx, S_H2IDX, (size_t)p * m);
@@ -379,7 +384,8 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     } ex;
     if (idx_panel) {
       const unsigned hc = std::thread::hardware_concurrency();
-      const int W = (int)std::max(1u, std::min(16u, hc > 1 ? hc - 1 : 1u));
+      int W = (int)std::max(1u, std::min(16u, hc > 1 ? hc - 1 : 1u));
+      if (const char* ht = getenv("BLMM_B200_HOST_THREADS")) W = std::max(1, std::min(64, atoi(ht)));
       const uint8_t* hI = ctx->h_idx;
       const double* grid = o->h2_grid;
       for (int w = 0; w < W; ++w)

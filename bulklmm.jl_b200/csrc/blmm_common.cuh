@@ -60,6 +60,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Counter arrive for "last consumer refills the stage": acq_rel at CTA scope orders this warp's shared-memory
+// reads of the stage before the increment and the last arriver's bulk copy after it — what the separate
+// __threadfence_block() (a sequentially consistent MEMBAR) + relaxed atomic paid more for.
+__device__ __forceinline__ int smem_counter_arrive(int* cnt) {
+  int old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
+  return old;
+}
+
 // 1-D bulk asynchronous copy global -> shared through the TMA engine (SASS: UBLKCP), completion
 // counted in bytes on an mbarrier.  dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

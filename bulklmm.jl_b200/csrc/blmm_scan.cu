@@ -406,8 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
       // of iteration it + NS, so the copy is in flight as early as the ring allows.
       if (lane == 0) {
         if (last_of_tt && last_k) mbar_arrive(top_empty);
-        __threadfence_block();
-        if (atomicAdd(&rel_cnt[s], 1) == NWARPS - 1) {
+        if (smem_counter_arrive(&rel_cnt[s]) == NWARPS - 1) {
           rel_cnt[s] = 0;
           if (it + NS < total_it) {
             int ntt = tt, nmt = mt, nkk = kk;
@@ -496,12 +495,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
           }
         }
         if (COLMAX) {
-          double cmax = fmax(fmax(acc[0][b][cc], acc[1][b][cc]), fmax(acc[2][b][cc], acc[3][b][cc]));
-          cmax = fmax(cmax, 0.0);
-          cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, 4));
-          cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, 8));
-          cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, 16));
-          if (g == 0 && Mc) atomic_max_nonneg(Mc, cmax + 0.0);
+          // maximum on the bit patterns (LODs are >= 0, so integer order = numeric order; a NaN is the largest
+          // and propagates like Julia's maximum): integer pipe only — this runs outside the group's turn, where
+          // FP64 instructions would sit behind the other group's DMMAs
+          long long cm = max(max(__double_as_longlong(acc[0][b][cc]), __double_as_longlong(acc[1][b][cc])),
+                             max(__double_as_longlong(acc[2][b][cc]), __double_as_longlong(acc[3][b][cc])));
+          cm = max(cm, 0LL);  // -0.0 and anything negative count as 0
+          cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, 4));
+          cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
+          cm = max(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
+          if (g == 0 && Mc) atomicMax(reinterpret_cast<unsigned long long*>(Mc), (unsigned long long)cm);
         }
       }
     if (++mt == n_mt) {

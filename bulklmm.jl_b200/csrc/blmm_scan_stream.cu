@@ -200,8 +200,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
         // Release the stage; the last of the ST_WARPS consumers refills it with iteration it + NS.
         __syncwarp();
         if (lane == 0) {
-          __threadfence_block();
-          if (atomicAdd(&rel_cnt[s], 1) == ST_WARPS - 1) {
+          if (smem_counter_arrive(&rel_cnt[s]) == ST_WARPS - 1) {
             rel_cnt[s] = 0;
             if (it + NS < total_it) issue_stage(s, it + NS);
           }

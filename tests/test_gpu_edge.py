@@ -164,10 +164,13 @@ def test_full_size_properties(engine):
     assert rel(r.L[:, cols], ref0.L) < 1e-8
 
 
-def test_alt_grid_host_chunked_copyback(engine):
+@pytest.mark.parametrize("transfer", ["index", "f64"])
+def test_alt_grid_host_chunked_copyback(engine, monkeypatch, transfer):
     """m >= 2048 traits through HOST buffers: the alt-grid scan runs in 8 trait-tile chunks whose columns
     are copied back on a second stream while the next chunk is scanned — results must be identical to the
     oracle (and to the same call with a padded leading dimension)."""
+    monkeypatch.setenv("BLMM_B200_H2_TRANSFER", transfer)  # default: index only for panels of >= 1e8 entries
+    monkeypatch.setenv("BLMM_B200_HOST_THREADS", "3")
     Y, G, K, Ut, lam, dec = make(79, 70, 2101, seed=31)
     a = bulkscan_alt_grid(Y, G, K, GRID, decomposition=dec, engine=engine)
     ref = orc.bulkscan_alt_grid(Y, G, K, GRID, Ut=Ut, lam=lam)
