@@ -236,7 +236,9 @@ void run_scan(blmm_ctx* ctx, ScanParams P) {
   P.logtab = reinterpret_cast<const double*>(ctx->buf[S_LOGTAB]);
   if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   if (P.nq <= scan_max_nq(P.nk)) {
-    ctx->launches += launch_scan(P, ctx->sm_count, ctx->stream);
+    const int launched = launch_scan(P, ctx->sm_count, ctx->stream);
+    if (!launched) throw Fail{BLMM_E_INVALID, "scan kernel: unsupported parameter combination"};
+    ctx->launches += launched;
   } else {
     // n too large for the shared-memory-resident trait tile: same arithmetic, K streamed
     static_assert(SCAN_TT == 128 && SCAN_MT == 64, "packing shared with the streamed GRID kernel");
@@ -314,7 +316,7 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     double* et = ws<double>(ctx, S_ET, (size_t)nk * tcol_pad);
     ctx->launches += launch_alt_scalars(ell, rss, ellmax, m, tcol_pad, nk, R.n, e, et, ctx->stream);
     double* Top = ws<double>(ctx, S_TOP, (size_t)R.n_pad * tcol_pad);
-    ctx->launches += launch_pack_traits(Yr, nullptr, m, tcol_pad, R.n_pad, Top, ctx->stream);
+    ctx->launches += launch_pack_traits(Yr, nullptr, m, tcol_pad, R.n_pad, nullptr, Top, ctx->stream);
     P.Top = Top;
     P.e = e;
     P.et = et;
@@ -333,7 +335,11 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     ctx->launches += launch_null_bins(best, rss, m, nk, SCAN_TT, tcol_pad, bin_count, bin_start, bin_cursor,
                                       tile_k0, n_tiles, col_map, et, ctx->stream);
     double* Top = ws<double>(ctx, S_TOP, (size_t)R.n_pad * tcol_pad);
-    ctx->launches += launch_pack_traits(Yr, col_map, m, tcol_pad, R.n_pad, Top, ctx->stream);
+    // shared-memory-resident kernel: 1/rss is folded into the packed trait columns (one FP64 operation less
+    // per output); the K-streamed fallback for n > 100 keeps it as the per-column scalar et
+    const bool fold = R.nq <= scan_max_nq(1);
+    ctx->launches += launch_pack_traits(Yr, col_map, m, tcol_pad, R.n_pad, fold ? et : nullptr, Top, ctx->stream);
+    P.et_folded = fold ? 1 : 0;
     P.Top = Top;
     P.et = et;
     P.tile_k0 = tile_k0;
@@ -689,6 +695,7 @@ int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const 
   P.Top = Top;
   P.Mop = Mop;
   P.et = et1;
+  P.et_folded = (R.nq <= scan_max_nq(1)) ? 1 : 0;  // columns are normalised: v = 1 - d^2
   P.nq = R.nq;
   P.p = (int)p;
   P.p_pad = (int)p_pad;

@@ -75,9 +75,10 @@ int launch_null_bins(const int* best, const double* rss, int64_t m, int nk, int 
                      int* bin_count, int* bin_start, int* bin_cursor, int* tile_k0, int* n_tiles,
                      int* col_map, double* et, cudaStream_t stream);
 
-// Top[q][pos][kk] = Yr[col_map[pos]][q*KC+kk]  (identity map when col_map == nullptr; pads zero)
+// Top[q][pos][kk] = Yr[col_map[pos]][q*KC+kk]  (identity map when col_map == nullptr; pads zero), times
+// sqrt(scale2[pos]) when scale2 is given (one-k scans fold et = 1/rss into the trait operand: d^2 et = (d sqrt et)^2)
 int launch_pack_traits(const double* Yr, const int* col_map, int64_t m, int64_t tcol_pad, int n_pad,
-                       double* Top, cudaStream_t stream);
+                       const double* scale2, double* Top, cudaStream_t stream);
 
 // Permutation operand (transform_permute + column normalisation, src/transform_helpers.jl:94-102,
 // src/scan.jl:531-536): column 0 = z/||z||, column s>=1 = z[perm_idx[:,s-1]]/||z||, where z is the
@@ -119,6 +120,8 @@ struct ScanParams {
   const double* Mop;       // marker operand  [nk_total][nq][p_pad][KC]
   const double* e;         // [nk][tcol_pad] or nullptr (=> 1)
   const double* et;        // [nk][tcol_pad], required
+  int et_folded;           // e == nullptr only: et is already folded into the trait operand (columns scaled by
+                           // sqrt(et)), v = 1 - d^2; the K-streamed fallback kernel does not support it
   const int* tile_k0;      // per trait tile: first k (index into Mop); nullptr => 0
   const int* n_tiles_dev;  // device scalar: number of trait tiles in use; nullptr => n_tiles_t
   const int* col_map;      // [tcol_pad] packed column -> output column (-1 = padding); nullptr => identity

@@ -522,14 +522,17 @@ __global__ void bin_scatter_kernel(const int* __restrict__ best, const double* _
 }
 
 __global__ void pack_traits_kernel(const double* __restrict__ Yr, const int* __restrict__ col_map, int64_t m,
-                                   int64_t tcol_pad, int n_pad, int64_t total, double* __restrict__ Top) {
+                                   int64_t tcol_pad, int n_pad, int64_t total, const double* __restrict__ scale2,
+                                   double* __restrict__ Top) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int kk = (int)(idx % KC);
   const int64_t pos = (idx / KC) % tcol_pad;
   const int q = (int)(idx / (KC * tcol_pad));
   int64_t src = col_map ? (int64_t)col_map[pos] : (pos < m ? pos : -1);
-  Top[idx] = (src >= 0) ? Yr[src * n_pad + q * KC + kk] : 0.0;
+  double v = (src >= 0) ? Yr[src * n_pad + q * KC + kk] : 0.0;
+  if (scale2) v *= sqrt(scale2[pos]);
+  Top[idx] = v;
 }
 
 __global__ void pack_perms_kernel(const double* __restrict__ z, const double* __restrict__ rss,
@@ -661,10 +664,10 @@ int launch_null_bins(const int* best, const double* rss, int64_t m, int nk, int 
 }
 
 int launch_pack_traits(const double* Yr, const int* col_map, int64_t m, int64_t tcol_pad, int n_pad,
-                       double* Top, cudaStream_t stream) {
+                       const double* scale2, double* Top, cudaStream_t stream) {
   const int64_t total = (int64_t)n_pad * tcol_pad;
   pack_traits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(Yr, col_map, m, tcol_pad, n_pad, total,
-                                                                           Top);
+                                                                           scale2, Top);
   return 1;
 }
 

@@ -98,14 +98,15 @@ __device__ __forceinline__ double fast_lod(double v, const double2* __restrict__
   const double m = __hiloint2double(hi - (e << 20), lo);
   const double2 t = tab[(ix >> 11) & (LTAB - 1)];
   const double r = fma(m, t.x, -1.0);
-  double q = fma(r, 1.0 / 5.0, -1.0 / 4.0);
-  q = fma(q, r, 1.0 / 3.0);
-  q = fma(q, r, -1.0 / 2.0);
-  q = fma(q, r, 1.0);
-  const double lp = q * r;
+  // -(n/2) log10(e) * log1p(r) = r * (k1 + r (k2 + r (k3 + r (k4 + r k5)))), k_i = c_ln * (-1)^(i+1) / i: the
+  // scale is folded into the coefficients and the last multiply into the final FMA (8 FP64 operations in all)
+  double q = fma(r, c_ln * (1.0 / 5.0), c_ln * (-1.0 / 4.0));
+  q = fma(q, r, c_ln * (1.0 / 3.0));
+  q = fma(q, r, c_ln * (-1.0 / 2.0));
+  q = fma(q, r, c_ln);
   special |= (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
   // c_ln = -(n/2) log10(e), c_e = -(n/2) log10(2), t.y = -(n/2) * (-log10 rcp)
-  return fma(lp, c_ln, fma((double)e, c_e, t.y));
+  return fma(q, r, fma((double)e, c_e, t.y));
 }
 
 // IEEE results for the operands fast_lod flags: v = 0 (r^2 = 1) -> LOD = +inf (a subnormal v,
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
   const int total_it = (u1 - u0) * nk;
   constexpr uint32_t marker_chunk_bytes = MT * KC * 8;
   constexpr uint32_t trait_chunk_bytes = TT * KC * 8;
-  constexpr uint32_t stage_bytes = (uint32_t)NQ * marker_chunk_bytes + TT * 8 + (HAS_E ? TT * 8 : 0);
+  constexpr uint32_t stage_bytes = (uint32_t)NQ * marker_chunk_bytes + (HAS_E ? 2 * TT * 8 : 0);
 
   // Fill stage s with the operands of iteration (tt, mt, kk): the k-th marker tile and that k's
   // per-trait scalars.  Called by one thread; completion is counted on full[s].
@@ -191,8 +192,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
     for (int q = 0; q < NQ; ++q)
       bulk_g2s_hint(st + (size_t)q * MT * KC, src + (size_t)q * P.p_pad * KC, marker_chunk_bytes, &full[s], keep_policy);
     double* sc = st + (size_t)NQ * MT * KC;
-    bulk_g2s(sc + TT, P.et + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
-    if (HAS_E) bulk_g2s(sc, P.e + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
+    if (HAS_E) {
+      bulk_g2s(sc + TT, P.et + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
+      bulk_g2s(sc, P.e + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
+    }
   };
   // (tt, mt, kk) advanced by `steps` iterations
   auto advance = [&](int& tt, int& mt, int& kk, int steps) {
@@ -314,30 +317,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
       // other group multiplies they would sit behind its DMMA stream until it ends (measured: the pipe
       // serves two back-to-back DMMA warps and starves a third warp's DFMA), so they go here, in the
       // order the last k-step finishes the accumulators.  v overwrites the accumulator.
-      double ek[BT][2], etk[BT][2];  // per-k trait scalars for this lane's 2*BT trait columns
-      {
+      if (HAS_E) {
+        double ek[BT][2], etk[BT][2];  // per-k trait scalars for this lane's 2*BT trait columns
         const double* sc = ms + (size_t)NQ * MT * KC + wt * (8 * BT) + 2 * t;
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
-          if (HAS_E) {
-            const double2 v = *reinterpret_cast<const double2*>(sc + b * 8);
-            ek[b][0] = v.x; ek[b][1] = v.y;
-          } else {
-            ek[b][0] = ek[b][1] = 1.0;
-          }
+          const double2 v = *reinterpret_cast<const double2*>(sc + b * 8);
+          ek[b][0] = v.x; ek[b][1] = v.y;
           const double2 w = *reinterpret_cast<const double2*>(sc + TT + b * 8);
           etk[b][0] = w.x; etk[b][1] = w.y;
         }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < BT; ++b)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const double d = acc[a][b][cc];
+              acc[a][b][cc] = fma(-(d * d), etk[b][cc], ek[b][cc]);
+            }
+      } else {
+        // one-k scans: et = 1/rss is folded into the packed trait columns (ScanParams::et_folded), e = 1
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < BT; ++b)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              const double d = acc[a][b][cc];
+              acc[a][b][cc] = fma(-d, d, 1.0);
+            }
       }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < BT; ++b)
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const double d = acc[a][b][cc];
-            acc[a][b][cc] = fma(-(d * d), etk[b][cc], ek[b][cc]);
-          }
       // tmax! bookkeeping of this k: integer pipe only (strict `<` as `max .< to_compare`, on the bit
       // patterns: equivalent for the non-negative v that occur; a negative v (r^2 > 1 by rounding)
       // orders below every positive one, as it should)
@@ -581,7 +591,8 @@ extern "C" __attribute__((visibility("default"))) int blmm_debug_scan_trace(long
 #endif
 
 int launch_scan(const ScanParams& P, int sm_count, cudaStream_t stream) {
-  if ((!P.e && P.nk != 1) || (P.e && P.colmax)) return 0;  // combinations the kernel variants do not cover
+  // combinations the kernel variants do not cover
+  if ((!P.e && (P.nk != 1 || !P.et_folded)) || (P.e && P.colmax)) return 0;
   switch (P.nq) {
     case 1: launch_nq<1>(P, sm_count, stream); break;
     case 2: launch_nq<2>(P, sm_count, stream); break;
