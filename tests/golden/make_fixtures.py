@@ -6,6 +6,9 @@
                      (genotypes/phenotypes are listed in .MISSING_LARGE_BLOBS).
   oracle_small.npz : seeded synthetic genotypes/traits on that kinship and the oracle's outputs,
                      a regression pin for the oracle and a GPU parity case on a realistic K.
+  oracle_scan.npz  : the single-trait paths on the same kinship: scan (null, REML), scan with permutations (the
+                     0-based shuffle indices are part of the fixture), scan assumption="alt", bulkscan_null
+                     (per-trait Brent), lod2log10p and get_thresholds.
 """
 import os
 import sys
@@ -36,3 +39,22 @@ a = orc.bulkscan_alt_grid(Y, G, K, grid)
 np.savez_compressed(os.path.join(HERE, "oracle_small.npz"), Y=Y, G=G, null_L=r.L, null_h2=r.h2_null_list,
                     alt_L=a.L, alt_h2_panel=a.h2_panel)
 print("fixtures written", K.shape, K.min(), K.max())
+
+# ---- single-trait paths --------------------------------------------------------------------------
+Ut, lam = orc.decompose(K)
+y = Y[:, 3:4]
+Cv = synth.make_covar(79)[:, :1]
+s_null = orc.scan(y, G, K, covar=Cv, reml=True, Ut=Ut, lam=lam)
+perm_idx = orc.make_perm_indices(79, 64, 11)
+s_perm = orc.scan(y, G, K, permutation_test=True, perm_idx=perm_idx, Ut=Ut, lam=lam)
+s_alt = orc.scan(y, G[:, :60], K, assumption="alt", prior_variance=float(np.var(y, ddof=1)), prior_sample_size=0.1,
+                 Ut=Ut, lam=lam)
+b_null = orc.bulkscan_null(Y[:, :8], G, K, reml=True, prior_variance=0.0, Ut=Ut, lam=lam)
+thr = orc.get_thresholds(s_perm["L_perms"], [0.1, 0.05])
+np.savez_compressed(os.path.join(HERE, "oracle_scan.npz"), Ut=Ut, lam=lam, covar=Cv,
+                    null_lod=s_null["lod"], null_h2=s_null["h2_null"], null_sigma2=s_null["sigma2_e"],
+                    perm_idx=perm_idx, perm_lod=s_perm["lod"], perm_L=s_perm["L_perms"], perm_h2=s_perm["h2_null"],
+                    alt_lod=s_alt["lod"], alt_h2_each=s_alt["h2_each_marker"], alt_h2_null=s_alt["h2_null"],
+                    bnull_L=b_null.L, bnull_h2=b_null.h2_null_list,
+                    log10p=orc.lod2log10p(s_null["lod"], 1), thr=thr["thrs"])
+print("scan fixtures written")

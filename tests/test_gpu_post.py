@@ -100,3 +100,29 @@ def test_output_pvals_fused(engine):
         assert rel(r.log10Pvals_mat, orc.lod2log10p(np.maximum(plain.L, 0.0), 1)) < 1e-9
     r2 = bulkscan(Y, G, K, method="null-grid", output_pvals=True, chisq_df=2, engine=engine)
     assert rel(r2.log10Pvals_mat, orc.lod2log10p(np.maximum(r2.L, 0.0), 2)) < 1e-9
+
+
+def test_golden_single_trait_fixture(engine):
+    """The committed single-trait fixture (tests/golden/oracle_scan.npz) through the C-ABI, with the fixture's own
+    decomposition and shuffle indices: scan null (REML, one covariate), permutations, assumption="alt",
+    bulkscan_null, thresholds, p-values."""
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(gold, "oracle_scan.npz"))
+    s = np.load(os.path.join(gold, "oracle_small.npz"))
+    K = np.load(os.path.join(gold, "bxd_kinship.npy"))
+    Y, G = s["Y"], s["G"]
+    dec = (np.asfortranarray(z["Ut"].T), z["lam"])
+    y = Y[:, 3]
+    r = scan(y, G, K, covar=z["covar"], reml=True, decomposition=dec, engine=engine)
+    assert abs(r.h2_null - z["null_h2"]) < 1e-6 and rel(r.lod, z["null_lod"]) < 2e-5
+    rp = scan(y, G, K, permutation_test=True, perm_idx=z["perm_idx"], decomposition=dec, engine=engine)
+    assert abs(rp.h2_null - z["perm_h2"]) < 1e-6
+    assert rel(rp.lod, z["perm_lod"]) < 2e-5 and rel(rp.L_perms, z["perm_L"]) < 2e-5
+    assert rel(get_thresholds(rp.L_perms, [0.1, 0.05], engine=engine).thrs, z["thr"]) < 2e-5
+    ra = scan(y, G[:, :60], K, assumption="alt", prior_variance=float(np.var(y, ddof=1)), prior_sample_size=0.1,
+              decomposition=dec, engine=engine)
+    assert np.max(np.abs(ra.h2_each_marker - z["alt_h2_each"])) < 2e-6 and rel(ra.lod, z["alt_lod"]) < 1e-6
+    rb = bulkscan_null(Y[:, :8], G, K, reml=True, prior_variance=0.0, decomposition=dec, engine=engine)
+    assert np.max(np.abs(rb.h2_null_list - z["bnull_h2"])) < 1e-6 and rel(rb.L, z["bnull_L"]) < 2e-5
+    assert rel(lod2log10p(z["null_lod"], 1, engine=engine), z["log10p"]) < 1e-10

@@ -98,3 +98,34 @@ def test_golden_oracle_outputs_reproduce():
     a = orc.bulkscan_alt_grid(z["Y"], z["G"], K, grid)
     assert np.max(np.abs(a.L - z["alt_L"])) < 1e-10
     assert np.mean(a.h2_panel != z["alt_h2_panel"]) < 1e-3
+
+
+def test_golden_single_trait_paths_reproduce():
+    """tests/golden/oracle_scan.npz (make_fixtures.py): scan null / permutations / assumption="alt", bulkscan_null,
+    lod2log10p and get_thresholds on the real BXD kinship."""
+    z = np.load(os.path.join(GOLD, "oracle_scan.npz"))
+    s = np.load(os.path.join(GOLD, "oracle_small.npz"))
+    K = np.load(os.path.join(GOLD, "bxd_kinship.npy"))
+    Y, G = s["Y"], s["G"]
+    Ut, lam = z["Ut"], z["lam"]
+    y = Y[:, 3:4]
+    r = orc.scan(y, G, K, covar=z["covar"], reml=True, Ut=Ut, lam=lam)
+    assert np.allclose(r["lod"], z["null_lod"], rtol=1e-10, atol=1e-12) and abs(r["h2_null"] - z["null_h2"]) < 1e-9
+    rp = orc.scan(y, G, K, permutation_test=True, perm_idx=z["perm_idx"], Ut=Ut, lam=lam)
+    assert np.allclose(rp["L_perms"], z["perm_L"], rtol=1e-10, atol=1e-12)
+    assert np.allclose(orc.get_thresholds(rp["L_perms"], [0.1, 0.05])["thrs"], z["thr"], rtol=1e-12)
+    ra = orc.scan(y, G[:, :60], K, assumption="alt", prior_variance=float(np.var(y, ddof=1)), prior_sample_size=0.1,
+                  Ut=Ut, lam=lam)
+    assert np.allclose(ra["lod"], z["alt_lod"], rtol=1e-9, atol=1e-10)
+    assert np.allclose(ra["h2_each_marker"], z["alt_h2_each"], atol=1e-9)
+    assert np.allclose(orc.lod2log10p(z["null_lod"], 1), z["log10p"], rtol=1e-12)
+
+
+def test_lod2log10p_known_values():
+    """src/util.jl:199-206 against textbook chi-square quantiles: the 5 % / 1 % critical values of chi2(1), chi2(2)."""
+    ln10 = np.log(10.0)
+    for df, crit, p in ((1, 3.841458820694124, 0.05), (1, 6.634896601021213, 0.01), (2, 5.991464547107979, 0.05),
+                        (2, 9.210340371976182, 0.01)):
+        assert abs(orc.lod2log10p(crit / (2 * ln10), df) - (-np.log10(p))) < 1e-12
+    # far tail: log-space evaluation stays finite where log(sf) underflows
+    assert np.isfinite(orc.lod2log10p(500.0, 1)) and 501 < orc.lod2log10p(500.0, 1) < 502.5
