@@ -110,8 +110,14 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
     const int k0 = (MODE == MODE_GRID && P.tile_k0) ? P.tile_k0[tt] : 0;
     double* st = stages + (size_t)s * plan.stage_doubles;
     mbar_arrive_expect_tx(&full[s], marker_bytes + trait_bytes);
-    bulk_g2s(st, P.Mop + ((((size_t)(k0 + k) * nq + q) * P.p_pad) + (size_t)mt * MT) * KC, marker_bytes, &full[s]);
-    bulk_g2s(st + MT * KC, P.Xop + (((size_t)q * P.xcol_pad) + (size_t)tt * TCOLS) * KC, trait_bytes, &full[s]);
+    // L2 residency: a band's trait tiles are re-read every round of units for the whole sweep over the marker
+    // tiles (keep them), a marker chunk is read by the band's <= 8 CTAs within one round and then dead (let it
+    // go first).  Without the hints the streaming marker fills push the trait tiles out of a 63 MB L2
+    // partition at n = 1000 (ncu: 210 GB of DRAM reads for ~35 GB of operands).
+    bulk_g2s_hint(st, P.Mop + ((((size_t)(k0 + k) * nq + q) * P.p_pad) + (size_t)mt * MT) * KC, marker_bytes, &full[s],
+                  l2_evict_first_policy());
+    bulk_g2s_hint(st + MT * KC, P.Xop + (((size_t)q * P.xcol_pad) + (size_t)tt * TCOLS) * KC, trait_bytes, &full[s],
+                  l2_evict_last_policy());
   };
 
   if (tid == 0)
