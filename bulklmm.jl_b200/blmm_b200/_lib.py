@@ -63,6 +63,10 @@ SIGNATURES = {
     "blmm_lod2log10p": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                   C.c_void_p, C.c_int]),
     "blmm_thresholds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "blmm_read_csv": (C.c_int, [C.c_char_p, C.c_char, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]),
+    "blmm_free_matrix": (None, [C.c_void_p, C.c_int]),
+    "blmm_io_last_error": (C.c_char_p, []),
     "blmm_weight_kinship": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
 }
 

@@ -21,6 +21,8 @@ import ctypes as C
 from types import SimpleNamespace
 from typing import Optional, Sequence
 
+import os
+
 import numpy as np
 
 from . import _lib as L
@@ -480,3 +482,58 @@ def thresholds_from_max(max_lod: np.ndarray, signif_level: Sequence[float], engi
 def lod2log10p(lod, df: int = 1, engine: Optional[Engine] = None):
     """src/util.jl:199-206 on the device (blmm_lod2log10p)."""
     return (engine or default_engine()).lod2log10p(lod, df)
+
+
+# ---- data ingest (src/readData.jl) ------------------------------------------------------------------
+class DeviceMatrix:
+    """A column-major Float64 matrix in device memory owned by the library (blmm_read_csv with device >= 0):
+    `.ptr` goes straight into Engine.make_problem for BLMM_MEM_DEVICE calls."""
+
+    def __init__(self, ptr: int, rows: int, cols: int, device: int):
+        self.ptr, self.shape, self.device = ptr, (rows, cols), device
+
+    def free(self):
+        if self.ptr:
+            L.load().blmm_free_matrix(self.ptr, self.device)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def read_csv_matrix(path: str, skip_rows: int = 1, first_col: int = 0, col_step: int = 1, drop_last_cols: int = 0,
+                    delim: str = ",", device: Optional[int] = None):
+    """blmm_read_csv: numpy array (Fortran order) or, with `device=<gpu index>`, a DeviceMatrix."""
+    lib = L.load()
+    rows, cols, data = C.c_int64(0), C.c_int64(0), C.c_void_p(0)
+    dev = -1 if device is None else int(device)
+    st = lib.blmm_read_csv(os.fsencode(path), delim.encode()[:1], skip_rows, first_col, col_step, drop_last_cols, dev,
+                           C.byref(rows), C.byref(cols), C.byref(data))
+    if st != 0:
+        raise BlmmError(st, lib.blmm_io_last_error().decode())
+    if dev >= 0:
+        return DeviceMatrix(data.value, rows.value, cols.value, dev)
+    try:
+        n = rows.value * cols.value
+        arr = np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_double)), shape=(max(n, 1),))[:n].copy()
+    finally:
+        lib.blmm_free_matrix(data, -1)
+    return arr.reshape((rows.value, cols.value), order="F")
+
+
+def readBXDpheno(file: str, device: Optional[int] = None):
+    """src/readData.jl:159-161: skip the header line, drop the first (id) and last (sex) columns."""
+    return read_csv_matrix(file, skip_rows=1, first_col=1, col_step=1, drop_last_cols=1, device=device)
+
+
+def readBXDgeno(file: str, skipstart: int = 1, device: Optional[int] = None):
+    """src/readData.jl:163-165: `[:, 2:2:end]` of the data lines."""
+    return read_csv_matrix(file, skip_rows=skipstart, first_col=1, col_step=2, device=device)
+
+
+def readGenoProb_ExcludeComplements(file: str, device: Optional[int] = None):
+    """src/readData.jl:85-96: header of marker names, first column ids, then the odd probability columns."""
+    return read_csv_matrix(file, skip_rows=1, first_col=1, col_step=2, device=device)

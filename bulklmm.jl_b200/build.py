@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "blmm_b200", "lib")
 LIB = os.path.join(LIBDIR, "libblmm_b200.so")
-SOURCES = ["blmm_api.cu", "blmm_prep.cu", "blmm_fit.cu", "blmm_scan.cu", "blmm_scan_stream.cu", "blmm_post.cu"]
+SOURCES = ["blmm_api.cu", "blmm_prep.cu", "blmm_fit.cu", "blmm_scan.cu", "blmm_scan_stream.cu", "blmm_post.cu", "blmm_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-pthread"]
 

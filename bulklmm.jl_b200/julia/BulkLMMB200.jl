@@ -18,7 +18,7 @@ module BulkLMMB200
 using LinearAlgebra, Random, Statistics
 
 export bulkscan, bulkscan_null, bulkscan_null_grid, bulkscan_alt_grid, scan, calcKinship, transform_rotation,
-       get_thresholds, thresholds_from_max, lod2log10p
+       get_thresholds, thresholds_from_max, lod2log10p, readBXDpheno, readBXDgeno, readGenoProb_ExcludeComplements
 
 const libblmm = get(ENV, "BLMM_B200_LIB", "libblmm_b200.so")
 
@@ -304,5 +304,22 @@ function lod2log10p(lod::Array{Float64}, df::Int64 = 1; ctx::Context = default_c
         ctx.handle, lod, length(lod), 1, 0, 0, df, out, BLMM_MEM_HOST))
     return out
 end
+
+# ---- data ingest (src/readData.jl:85-96, 159-165): parsed by the library's host threads ----------------------
+function read_csv_matrix(file::AbstractString; skip_rows::Int64 = 1, first_col::Int64 = 0, col_step::Int64 = 1,
+                         drop_last_cols::Int64 = 0, dlm::AbstractChar = ',')
+    rows = Ref{Int64}(0); cols = Ref{Int64}(0); data = Ref{Ptr{Float64}}(C_NULL)
+    st = ccall((:blmm_read_csv, libblmm), Cint,
+               (Cstring, Cchar, Int64, Int64, Int64, Int64, Cint, Ref{Int64}, Ref{Int64}, Ref{Ptr{Float64}}),
+               file, Cchar(dlm), skip_rows, first_col, col_step, drop_last_cols, Cint(-1), rows, cols, data)
+    st == 0 || throw(error(unsafe_string(ccall((:blmm_io_last_error, libblmm), Cstring, ()))))
+    out = copy(unsafe_wrap(Array, data[], (rows[], cols[])))
+    ccall((:blmm_free_matrix, libblmm), Cvoid, (Ptr{Float64}, Cint), data[], Cint(-1))
+    return out
+end
+readBXDpheno(file::AbstractString) = read_csv_matrix(file; skip_rows = 1, first_col = 1, drop_last_cols = 1)
+readBXDgeno(file::AbstractString; skipstart = 1) = read_csv_matrix(file; skip_rows = skipstart, first_col = 1, col_step = 2)
+readGenoProb_ExcludeComplements(file::AbstractString; dlm::AbstractChar = ',') =
+    read_csv_matrix(file; skip_rows = 1, first_col = 1, col_step = 2, dlm = dlm)
 
 end # module

@@ -201,6 +201,21 @@ BLMM_API int blmm_thresholds(blmm_ctx* ctx, const double* maxlod, int64_t nperms
 BLMM_API int blmm_weight_kinship(blmm_ctx* ctx, int64_t n, const double* K, const double* w, double* K_out,
                         int mem_space);
 
+/* ---- data ingest ------------------------------------------------------------ */
+/* The delimited-text matrices the reference reads with readdlm, parsed by host threads into a column-major
+ * Float64 matrix: rows = data lines after `skip_rows`, columns = fields first_col, first_col + col_step, ... up to
+ * (not including) the last `drop_last_cols` fields (0-based field numbers).
+ *   readBXDpheno(file)                    src/readData.jl:159-161   skip 1, first_col 1, step 1, drop_last 1
+ *   readBXDgeno(file; skipstart = 1)      src/readData.jl:163-165   skip 1, first_col 1, step 2, drop_last 0
+ *   readGenoProb_ExcludeComplements(file) src/readData.jl:85-96     skip 1, first_col 1, step 2, drop_last 0
+ * device < 0: *data_out is host memory (malloc);  device >= 0: device memory on that GPU (one H2D copy), ready
+ * for BLMM_MEM_DEVICE calls.  Release with blmm_free_matrix(data, device).  Needs no context; the message of a
+ * failure (missing file, non-numeric field, ragged row) is returned by blmm_io_last_error() (thread-local).   */
+BLMM_API int blmm_read_csv(const char* path, char delim, int64_t skip_rows, int64_t first_col, int64_t col_step,
+                  int64_t drop_last_cols, int device, int64_t* rows_out, int64_t* cols_out, double** data_out);
+BLMM_API void blmm_free_matrix(double* data, int device);
+BLMM_API const char* blmm_io_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -746,3 +746,31 @@ def get_thresholds(L: np.ndarray, signif_level: Sequence[float]):
     peaks = np.max(L, axis=0)
     probs = 1.0 - np.asarray(signif_level, dtype=np.float64)
     return {"probs": probs, "thrs": np.quantile(peaks, probs)}
+
+
+# ----------------------------------------------------------------------------------------
+# readData.jl (the delimited-text readers either side of the scan path)
+# ----------------------------------------------------------------------------------------
+def _readdlm(file: str, skipstart: int):
+    rows = []
+    with open(file) as f:
+        for i, line in enumerate(f):
+            if i < skipstart or not line.strip():
+                continue
+            rows.append(line.rstrip("\r\n").split(","))
+    return rows
+
+
+def read_bxd_pheno(file: str) -> np.ndarray:
+    """src/readData.jl:159-161: readdlm(file, ','; skipstart=1)[:, 2:end-1]."""
+    return np.array([[float(x) for x in r[1:-1]] for r in _readdlm(file, 1)], dtype=np.float64)
+
+
+def read_bxd_geno(file: str, skipstart: int = 1) -> np.ndarray:
+    """src/readData.jl:163-165: readdlm(file, ','; skipstart)[:, 2:2:end]."""
+    return np.array([[float(x) for x in r[1::2]] for r in _readdlm(file, skipstart)], dtype=np.float64)
+
+
+def read_genoprob_exclude_complements(file: str) -> np.ndarray:
+    """src/readData.jl:85-96 with getmarkernames = getids = true: numeric block after header/ids, odd columns."""
+    return np.array([[float(x) for x in r[1:][0::2]] for r in _readdlm(file, 1)], dtype=np.float64)

@@ -195,3 +195,33 @@ def test_alt_grid_host_chunked_copyback(engine, monkeypatch, transfer):
         engine.sync()
         assert np.array_equal(host.L, dL.cpu().numpy().T)
         assert np.array_equal(host.h2_panel, dH.cpu().numpy().T)
+
+
+def test_ingest_straight_to_device(engine, tmp_path):
+    """readBXDpheno / readGenoProb_ExcludeComplements with device=0: the parsed matrices land in device memory and feed
+    a device-resident scan without ever being host arrays on the caller's side; same LODs as the host path."""
+    import torch
+    from blmm_b200 import _lib as L, readBXDpheno, readGenoProb_ExcludeComplements
+    from test_ingest_cpu import write_geno, write_pheno
+    ppath, gpath = str(tmp_path / "pheno.csv"), str(tmp_path / "geno.csv")
+    Y = write_pheno(ppath, n=79, m=140, seed=5)
+    G = write_geno(gpath, n=79, p=90, seed=6)
+    K = synth.calc_kinship_host(G)
+    dY, dG = readBXDpheno(ppath, device=0), readGenoProb_ExcludeComplements(gpath, device=0)
+    assert dY.shape == Y.shape and dG.shape == G.shape
+    U, lam, _ = engine.decompose(K)
+    dev = torch.device("cuda:0")
+    dC = torch.ones(79, dtype=torch.float64, device=dev)
+    dU = torch.from_numpy(np.ascontiguousarray(U.T)).to(dev)
+    dl = torch.from_numpy(lam.copy()).to(dev)
+    dL = torch.empty((140, 90), dtype=torch.float64, device=dev)
+    dh = torch.empty(140, dtype=torch.float64, device=dev)
+    pr = engine.make_problem(79, 90, 140, 1, dY.ptr, dG.ptr, dC.data_ptr(), dU.data_ptr(), dl.data_ptr())
+    o, keep = engine.make_opts(method=L.METHOD_NULL_GRID, h2_grid=GRID, mem_space=L.MEM_DEVICE)
+    engine.bulkscan_raw(pr, o, dL.data_ptr(), dh.data_ptr())
+    engine.sync()
+    host = bulkscan_null_grid(readBXDpheno(ppath), readGenoProb_ExcludeComplements(gpath), K, GRID,
+                              decomposition=(U, lam), engine=engine)
+    assert np.array_equal(host.L, dL.cpu().numpy().T) and np.array_equal(host.h2_null_list, dh.cpu().numpy())
+    dY.free()
+    dG.free()
