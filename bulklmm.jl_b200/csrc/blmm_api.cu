@@ -23,7 +23,7 @@ using namespace blmm;
 enum Slot {
   S_Y_IN, S_G_IN, S_C_IN, S_U_IN, S_LAM, S_GRID, S_Y0, S_C0, S_G0, S_YR, S_W, S_SW, S_Q, S_SLW, S_LDS,
   S_ELL, S_RSS, S_BEST, S_ELLMAX, S_MOP, S_TOP, S_E, S_ET, S_BINS, S_TILEK0, S_COLMAP, S_L, S_H2P, S_H2V,
-  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_LOGTAB, S_XOP, S_DYINV, S_PVAL, S_OBSW, S_UW, S_SORT, S_SORTTMP, S_PROBS, S_H2IDX,
+  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_LOGTAB, S_XOP, S_DYINV, S_PVAL, S_OBSW, S_UW, S_SORT, S_SORTTMP, S_PROBS, S_H2IDX, S_UNITCTR,
   S_COUNT
 };
 
@@ -228,6 +228,13 @@ double* pvals_after_scan(blmm_ctx* ctx, const blmm_opts* o, const double* dL, in
   return dP;
 }
 
+// zeroed device counter for the stream kernels' dynamic unit scheduler
+unsigned long long* fresh_unit_counter(blmm_ctx* ctx) {
+  unsigned long long* c = ws<unsigned long long>(ctx, S_UNITCTR, 1);
+  CUDA_TRY(cudaMemsetAsync(c, 0, sizeof(unsigned long long), ctx->stream));
+  return c;
+}
+
 void run_scan(blmm_ctx* ctx, ScanParams P) {
   if (!ctx->buf[S_LOGTAB]) {
     double* tab = ws<double>(ctx, S_LOGTAB, scan_logtab_doubles());
@@ -248,6 +255,7 @@ void run_scan(blmm_ctx* ctx, ScanParams P) {
     Q.H2 = P.H2; Q.colmax = P.colmax; Q.ldL = P.ldL; Q.nq = P.nq; Q.p = P.p; Q.p_pad = P.p_pad; Q.m = P.m;
     Q.xcol_pad = P.tcol_pad; Q.tcol_pad = P.tcol_pad; Q.n_tt = P.n_tiles_t; Q.nk = P.nk;
     Q.argmax_mode = P.argmax_mode; Q.half_n = P.half_n;
+    Q.unit_counter = fresh_unit_counter(ctx);  // n > 100: operands beyond L2 are the normal case here
     ctx->launches += launch_scan_stream_grid(Q, ctx->sm_count, ctx->stream);
   }
   if (ctx->profiling) {
@@ -587,6 +595,12 @@ int bulkscan_exact(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, do
   P.n_tt = (int)n_tt;
   P.nk = 1;
   P.half_n = (double)R.n / 2.0;
+  if (const char* b = getenv("BLMM_STREAM_BAND")) P.band = atoi(b);  // development knob (L2 rasterisation study)
+  // dynamic unit hand-out when the operands do not fit in L2 (it costs one global atomic per unit)
+  const double operand_bytes = 8.0 * R.n_pad * ((double)p_pad + (double)xcol_pad);
+  bool dynamic = operand_bytes > 100e6;
+  if (const char* d = getenv("BLMM_STREAM_DYNAMIC")) dynamic = d[0] == '1';  // test hook: force either scheduler
+  P.unit_counter = dynamic ? fresh_unit_counter(ctx) : nullptr;
   if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   ctx->launches += launch_scan_exact(P, R.c, ctx->sm_count, ctx->stream);
   if (ctx->profiling) {

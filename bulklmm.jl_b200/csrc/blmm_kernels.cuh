@@ -181,6 +181,8 @@ struct StreamParams {
   int64_t m;               // output columns
   int64_t xcol_pad;        // operand columns of Xop
   int64_t tcol_pad;        // GRID: padded packed-trait count (= xcol_pad)
+  int band;                // trait tiles per rasterisation band (0 = default)
+  unsigned long long* unit_counter;  // device scalar, zero at launch: dynamic unit scheduler (set by the launchers' caller)
   int n_tt;                // trait tiles (EXACT: 64 traits each; GRID: stream_grid_trait_tile())
   int nk;                  // GRID: k-list length
   int argmax_mode;

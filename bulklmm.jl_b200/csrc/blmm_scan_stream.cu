@@ -33,7 +33,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int GRID_MAX = 256;
 constexpr int ST_TG = 8;                  // warps along the trait dimension
 constexpr int ST_WARPS = 2 * ST_TG;       // x 2 along the marker dimension
-constexpr int BAND = 8;                   // trait tiles per rasterisation band
+constexpr int BAND_DEFAULT = 8;           // trait tiles per rasterisation band (StreamParams::band overrides)
 constexpr size_t ST_FIXED_SMEM = (size_t)LOGTAB_N * 16 + GRID_MAX * 8 + 128;
 
 enum { MODE_EXACT = 0, MODE_GRID = 1 };
@@ -59,13 +59,22 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
   constexpr int TCOLS = ST_TG * 8 * NB;  // operand columns per CTA tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const StreamPlan plan = stream_plan(NB, MA);
-  const int NS = plan.nstage;
+  // ring depth, capped by the items of one unit so that the prefetch never looks more than one unit ahead
+  const int ipu_cap = ((MODE == MODE_GRID) ? P.nk : 1) * P.nq;
+  const int NS = plan.nstage < ipu_cap ? plan.nstage : ipu_cap;
   double* stages = reinterpret_cast<double*>(smem_raw);
   double2* logtab = reinterpret_cast<double2*>(stages + NS * plan.stage_doubles);
   double* grid_s = reinterpret_cast<double*>(logtab + LOGTAB_N);
   uint64_t* full = reinterpret_cast<uint64_t*>(grid_s + GRID_MAX);  // [4]
   int* rel_cnt = reinterpret_cast<int*>(full + 4);                  // [4]
 
+  // Units are handed out dynamically (one atomic per unit): CTAs that become free take CONSECUTIVE units, so the
+  // CTAs sharing a marker tile stream it within microseconds of each other and it is read from DRAM once.  With a
+  // static round-robin the persistent CTAs drift apart over thousands of rounds and every CTA fetched its own copy
+  // (ncu at n = 1000: 212 GB of DRAM reads, = units x marker tile, whatever the band size).  uq[r & 3] is the unit
+  // of this CTA's r-th turn (fetched two turns ahead: the stage prefetch crosses into the next unit and warps may be a
+  // unit apart).
+  volatile long long* uq = reinterpret_cast<volatile long long*>(full + 8);  // inside the 128-byte barrier block
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -74,6 +83,8 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
       rel_cnt[s] = 0;
     }
     mbar_fence_init();
+    for (int o = 0; o < 3; ++o)
+      uq[o] = P.unit_counter ? (long long)atomicAdd(P.unit_counter, 1ULL) : (long long)blockIdx.x + (long long)o * gridDim.x;
   }
   if (tid < LOGTAB_N) logtab[tid] = reinterpret_cast<const double2*>(P.logtab)[tid];
   if (MODE == MODE_GRID && P.grid && tid < P.ngrid) grid_s[tid] = P.grid[tid];
@@ -84,14 +95,12 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
   const int nq = P.nq;
   const int nk = (MODE == MODE_GRID) ? P.nk : 1;
   const int64_t units = (int64_t)n_tt * n_mt;
-  const int64_t G = gridDim.x, b0 = blockIdx.x;
-  const int R = (b0 < units) ? (int)((units - b0 + G - 1) / G) : 0;
-  const int64_t total_it = (int64_t)R * nk * nq;
+  const int64_t ipu = (int64_t)nk * nq;  // ring items per unit
   constexpr uint32_t marker_bytes = MT * KC * 8;
   constexpr uint32_t trait_bytes = TCOLS * KC * 8;
 
-  auto decode = [&](int r, int& tt, int& mt) {
-    const int64_t u = b0 + (int64_t)r * G;
+  const int BAND = P.band > 0 ? P.band : BAND_DEFAULT;
+  auto decode = [&](int64_t u, int& tt, int& mt) {
     const int64_t per_band = (int64_t)BAND * n_mt;
     const int band = (int)(u / per_band);
     const int rem = (int)(u - (int64_t)band * per_band);
@@ -100,13 +109,16 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
     mt = rem / bw;
     tt = band * BAND + rem % bw;
   };
-  // Fill stage s with the operands of flat iteration `item` = ((r * nk) + k) * nq + q.
+  // Fill stage s with the operands of flat iteration `item` = ((r * nk) + k) * nq + q of this CTA's r-th unit
+  // (r is the current or the next turn); nothing to do past the last unit.
   auto issue_stage = [&](int s, int64_t item) {
     const int q = (int)(item % nq);
     const int64_t rk = item / nq;
     const int k = (int)(rk % nk);
+    const int64_t u = uq[(rk / nk) & 3];
+    if (u >= units) return;
     int tt, mt;
-    decode((int)(rk / nk), tt, mt);
+    decode(u, tt, mt);
     const int k0 = (MODE == MODE_GRID && P.tile_k0) ? P.tile_k0[tt] : 0;
     double* st = stages + (size_t)s * plan.stage_doubles;
     mbar_arrive_expect_tx(&full[s], marker_bytes + trait_bytes);
@@ -121,7 +133,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
   };
 
   if (tid == 0)
-    for (int i = 0; i < NS && i < total_it; ++i) issue_stage(i, i);
+    for (int i = 0; i < NS; ++i) issue_stage(i, i);
 
   const int g = lane >> 2, t = lane & 3;
   const int wm = warp / ST_TG;  // marker half (0..1)
@@ -132,9 +144,18 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
   int64_t it = 0;
   int s = 0;
   uint32_t sphase = 0;
-  for (int r = 0; r < R; ++r) {
+  for (int r = 0;; ++r) {
+    const int64_t u = uq[r & 3];
+    if (u >= units) break;
+    // Fetch the unit two turns ahead.  Warps are at most one unit apart in either direction of warp 0 (the ring is
+    // no longer than a unit), so ordinals r-1 .. r+1 are being read while r+2 is written: four slots, and the
+    // fetch runs two ahead so that a warp that is a unit AHEAD of warp 0 already finds its next unit.
+    // (unit_counter == nullptr: static round-robin, for problems whose operands fit in L2 anyway)
+    if (tid == 0 && r > 0)
+      uq[(r + 2) & 3] = P.unit_counter ? (long long)atomicAdd(P.unit_counter, 1ULL)
+                                       : (long long)blockIdx.x + (long long)(r + 2) * gridDim.x;
     int tt, mt;
-    decode(r, tt, mt);
+    decode(u, tt, mt);
 
     double vmin[MA][NB][2];       // GRID: running minimum;  EXACT: unused
     uint32_t cnt[(MA * NB * 2 + 3) / 4];
@@ -208,7 +229,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
         if (lane == 0) {
           if (smem_counter_arrive(&rel_cnt[s]) == ST_WARPS - 1) {
             rel_cnt[s] = 0;
-            if (it + NS < total_it) issue_stage(s, it + NS);
+            issue_stage(s, it + NS);
           }
         }
         if (++s == NS) {

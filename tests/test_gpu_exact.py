@@ -163,3 +163,23 @@ def test_scan_alt_per_marker_variance_components(engine, reml, ncov):
     assert np.max(np.abs(r.lod - ref["lod"]) / np.maximum(1.0, np.abs(ref["lod"]))) < 1e-6
     with pytest.raises(Exception, match="Permutation test option currently is not supported"):
         scan(y, G, K, assumption="alt", permutation_test=True, engine=engine)
+
+
+@pytest.mark.parametrize("dynamic", ["1", "0"])
+def test_null_exact_many_units_equals_sharded(engine, monkeypatch, dynamic):
+    """More (trait tile x marker tile) units than SMs: the K-streamed kernel hands units to CTAs dynamically and every
+    CTA works through several of them.  The whole scan must equal, bit for bit, the concatenation of two half scans
+    (each with at most one unit per CTA), and the oracle on a sample of traits."""
+    monkeypatch.setenv("BLMM_STREAM_DYNAMIC", dynamic)  # default: dynamic only when the operands exceed L2
+    Y, G, K = synth.make_problem(79, 1400, 640, seed_g=71, seed_y=72)
+    Ut, lam = orc.decompose(K)
+    dec = (np.asfortranarray(Ut.T), lam)
+    whole = bulkscan_null(Y, G, K, reml=True, prior_variance=0.0, decomposition=dec, engine=engine)
+    a = bulkscan_null(Y[:, :320], G, K, reml=True, prior_variance=0.0, decomposition=dec, engine=engine)
+    b = bulkscan_null(Y[:, 320:], G, K, reml=True, prior_variance=0.0, decomposition=dec, engine=engine)
+    assert np.array_equal(whole.L, np.hstack([a.L, b.L]))
+    assert np.array_equal(whole.h2_null_list, np.concatenate([a.h2_null_list, b.h2_null_list]))
+    idx = [0, 63, 64, 319, 320, 639]
+    ref = orc.bulkscan_null(Y[:, idx], G, K, reml=True, prior_variance=0.0, Ut=Ut, lam=lam)
+    assert np.max(np.abs(whole.h2_null_list[idx] - ref.h2_null_list)) < 1e-6
+    assert np.max(np.abs(whole.L[:, idx] - ref.L) / np.maximum(1.0, np.abs(ref.L))) < 2e-5
