@@ -593,6 +593,8 @@ extern "C" __attribute__((visibility("default"))) int blmm_debug_scan_trace(long
 int launch_scan(const ScanParams& P, int sm_count, cudaStream_t stream) {
   // combinations the kernel variants do not cover
   if ((!P.e && (P.nk != 1 || !P.et_folded)) || (P.e && P.colmax)) return 0;
+  // the kernel indexes its (unit, k) iterations with 32-bit integers
+  if ((int64_t)P.n_tiles_t * (P.p_pad / MT) * (int64_t)(P.nk > 0 ? P.nk : 1) >= 2147483647LL) return 0;
   switch (P.nq) {
     case 1: launch_nq<1>(P, sm_count, stream); break;
     case 2: launch_nq<2>(P, sm_count, stream); break;
