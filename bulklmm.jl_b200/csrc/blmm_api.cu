@@ -364,8 +364,11 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     // second stream while the next chunk is scanned.  The h2 panel holds one of <= 255 grid values per
     // entry, so it crosses PCIe as one-byte grid indices (1/8 of the bytes) into pinned staging and is
     // expanded to grid[index] in the caller's Float64 array by host threads while later chunks copy.
-    const int nchunk = 8;
     const int n_tiles = P.n_tiles_t;
+    // PCIe is the bottleneck, so what matters is how soon the first copy starts and how little expansion is left
+    // after the last one: more, smaller chunks for big panels
+    constexpr int MAX_CHUNK = 16;
+    const int nchunk = n_tiles >= 64 ? MAX_CHUNK : 8;
     // Worth it when the panel is large (PCIe time saved > host expansion time): >= 1e8 entries by default.
     // BLMM_B200_H2_TRANSFER = index | f64 overrides; BLMM_B200_HOST_THREADS sets the expansion thread count
     // (default min(16, cores - 1); several ranks sharing one host should divide the cores between them).
@@ -383,7 +386,7 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
         ctx->h_idx_cap = (size_t)p * m;
       }
     }
-    int64_t cbeg[nchunk + 1];
+    int64_t cbeg[MAX_CHUNK + 1];
     for (int ch = 0; ch <= nchunk; ++ch)
       cbeg[ch] = std::min<int64_t>((int64_t)((int64_t)n_tiles * ch / nchunk) * SCAN_TT, m);
     // expansion workers: worker w takes its slice of the columns of every chunk as the chunk lands
