@@ -8,10 +8,10 @@
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ void dmma0(double& c0, double& c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};" : "=d"(c0), "=d"(c1) : "d"(a), "d"(b), "d"(0.0));
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%4};" : "=d"(c0), "=d"(c1) : "d"(a), "d"(b), "d"(0.0));
 }
 
 constexpr int KC = 20, NQ = 4, MT = 64, TT = 128;
