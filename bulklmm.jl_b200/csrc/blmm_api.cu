@@ -301,8 +301,17 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   // null-grid: h2_null_list is written straight into the caller's array in device mode
   double* h2v = nullptr;
   if (!alt && h2_out) h2v = (ms == BLMM_MEM_DEVICE) ? h2_out : ws<double>(ctx, S_H2V, m);
+  // alt-grid: the statistics kernel also writes the packed trait operand and the per-k scalars when it can
+  TraitFuse fuse{nullptr, nullptr, nullptr, 0, false};
+  if (alt) {
+    fuse.tcol_pad = round_up(m, SCAN_TT);
+    fuse.e = ws<double>(ctx, S_E, (size_t)nk * fuse.tcol_pad);
+    fuse.et = ws<double>(ctx, S_ET, (size_t)nk * fuse.tcol_pad);
+    fuse.Top = ws<double>(ctx, S_TOP, (size_t)R.n_pad * fuse.tcol_pad);
+  }
   ctx->launches += launch_trait_stats(R.Y0, m, R.n, R.n_pad, R.c, nk, wc, lik_of(o), d_grid, Yr, ell, rss, best,
-                                      ellmax, h2v, alt ? nullptr : bin_count, ctx->d_flags, ctx->stream);
+                                      ellmax, h2v, alt ? nullptr : bin_count, ctx->d_flags, ctx->stream,
+                                      alt ? &fuse : nullptr);
 
   ScanParams P{};
   P.Mop = Mop;
@@ -319,12 +328,12 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   P.ldL = (ms == BLMM_MEM_DEVICE) ? ld : p;
   double* dH = nullptr;
   if (alt) {
-    const int64_t tcol_pad = round_up(m, SCAN_TT);
-    double* e = ws<double>(ctx, S_E, (size_t)nk * tcol_pad);
-    double* et = ws<double>(ctx, S_ET, (size_t)nk * tcol_pad);
-    ctx->launches += launch_alt_scalars(ell, rss, ellmax, m, tcol_pad, nk, R.n, e, et, ctx->stream);
-    double* Top = ws<double>(ctx, S_TOP, (size_t)R.n_pad * tcol_pad);
-    ctx->launches += launch_pack_traits(Yr, nullptr, m, tcol_pad, R.n_pad, nullptr, Top, ctx->stream);
+    const int64_t tcol_pad = fuse.tcol_pad;
+    double *e = fuse.e, *et = fuse.et, *Top = fuse.Top;
+    if (!fuse.done) {
+      ctx->launches += launch_alt_scalars(ell, rss, ellmax, m, tcol_pad, nk, R.n, e, et, ctx->stream);
+      ctx->launches += launch_pack_traits(Yr, nullptr, m, tcol_pad, R.n_pad, nullptr, Top, ctx->stream);
+    }
     P.Top = Top;
     P.e = e;
     P.et = et;

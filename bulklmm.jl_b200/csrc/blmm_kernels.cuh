@@ -50,10 +50,20 @@ struct LikParams {  // wls / wls_multivar scalars, src/wls.jl:72-92, 150-170
 //   rss  : [nk][m] weighted residual sum of squares (= squared norm of the residualised trait)
 //   best : [m] first arg-max over k of ell (findmax, src/bulkscan_helpers.jl:204-211)
 //   ellmax: [m] max_k ell;   h2_out (optional): grid[best];   bin_count (optional): histogram of best
+// `fuse` (optional, alt-grid): also produce what launch_alt_scalars + launch_pack_traits (identity column map)
+// would — Top[q][j][kk], e[k][j], et[k][j] for j < tcol_pad (pads: 0, 1, 0) — when the kernel in use can (the
+// table form with all grid points in one lane batch); fuse->done tells the caller whether it did.
+struct TraitFuse {
+  double* Top;
+  double* e;
+  double* et;
+  int64_t tcol_pad;
+  bool done;
+};
 int launch_trait_stats(const double* Y0, int64_t m, int n, int n_pad, int c, int nk, WeightConsts wc,
                        LikParams lik, const double* grid_dev, double* Yr, double* ell, double* rss,
                        int* best, double* ellmax, double* h2_out, int* bin_count, int* flags,
-                       cudaStream_t stream);
+                       cudaStream_t stream, TraitFuse* fuse = nullptr);
 
 // One warp per marker: x = P_k (sw_k .* g_i) / ||P_k (sw_k .* g_i)||  (the normalised X00 column of
 // weighted_liteqtl + computeR_LMM, src/bulkscan_helpers.jl:175-201, 47-64).

@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
     trait_stats_table_kernel(const double* __restrict__ Y0, int64_t m, int n, int n_pad, int c, int nk, WeightConsts wc,
                              LikParams lik, const double* __restrict__ grid_dev, double* __restrict__ Yr,
                              double* __restrict__ ell, double* __restrict__ rss_out, int* __restrict__ best,
-                             double* __restrict__ ellmax, double* __restrict__ h2_out, int* bin_count, int* flags) {
+                             double* __restrict__ ellmax, double* __restrict__ h2_out, int* bin_count, int* flags,
+                             TraitFuse fuse) {
   extern __shared__ double smem[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = 32 / (1 + c);  // grid points per batch of 32 lane slots
@@ -371,7 +372,17 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
   double* yb = ybase + (int64_t)wid * n_pad;
   const double* sw1 = wc.sw + (int64_t)nk * n_pad;
   const double* Qo = wc.Q + (int64_t)nk * c * n_pad;
-  for (int64_t j = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wid; j < m; j += (int64_t)gridDim.x * WARPS_PER_BLOCK) {
+  const int64_t jend = fuse.Top ? fuse.tcol_pad : m;
+  for (int64_t j = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wid; j < jend; j += (int64_t)gridDim.x * WARPS_PER_BLOCK) {
+    if (j >= m) {
+      // padding columns of the packed operand and of the per-k scalars
+      for (int l = lane; l < n_pad; l += 32) fuse.Top[((int64_t)(l / KC) * fuse.tcol_pad + j) * KC + (l % KC)] = 0.0;
+      for (int k = lane; k < nk; k += 32) {
+        fuse.e[(int64_t)k * fuse.tcol_pad + j] = 1.0;
+        fuse.et[(int64_t)k * fuse.tcol_pad + j] = 0.0;
+      }
+      continue;
+    }
     for (int l = lane; l < n_pad; l += 32) yb[l] = Y0[j * n_pad + l];
     __syncwarp();
     double coef[MAXC];
@@ -380,10 +391,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
       const double y = proj_elem(yb, sw1, Qo, n_pad, c, l, coef);  // reads only this lane's element of yb
       yb[l] = y;
       Yr[j * n_pad + l] = y;
+      if (fuse.Top) fuse.Top[((int64_t)(l / KC) * fuse.tcol_pad + j) * KC + (l % KC)] = y;
     }
     __syncwarp();
     double bestv = -INFINITY;
     int bestk = 0x7fffffff;
+    double ll_mine = 0.0, rss_mine = 1.0;  // lane k's values (single batch), for the fused alt-grid scalars
     for (int bt = 0; bt < nbatch; ++bt) {
       const double* Tb = T + (size_t)bt * n_pad * 32 + lane;
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -408,6 +421,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
       const int kc = valid ? k : 0;
       const double ll = null_loglik(rss, wc.slw[kc], wc.lds[kc], n, c, lik, nullptr);
       if (valid) {
+        ll_mine = ll;
+        rss_mine = rss;
         ell[(int64_t)k + j * nk] = ll;
         rss_out[(int64_t)k * m + j] = rss;
         if (!(sqrt(rss) > DBL_EPSILON)) atomicExch(&flags[FLAG_ZERO_NORM], 1);
@@ -426,6 +441,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
         bestv = ov;
         bestk = ok;
       }
+    }
+    if (fuse.Top && lane < nk) {
+      // alt-grid scalars (launch_alt_scalars): e = exp(-2 (ell_k - max_k ell) / n), et = e / rss_k; one batch, so
+      // lane k still holds its own ell and rss
+      const double ev = exp(-(ll_mine - bestv) * (2.0 / (double)n));
+      fuse.e[(int64_t)lane * fuse.tcol_pad + j] = ev;
+      fuse.et[(int64_t)lane * fuse.tcol_pad + j] = ev / rss_mine;
     }
     if (lane == 0) {
       if (bestk == 0x7fffffff) bestk = 0;  // every log-likelihood NaN: as findmax on NaNs, first index
@@ -606,7 +628,8 @@ int launch_weight_consts(const double* h2_dev, int nk, const double* lambda, con
 int launch_trait_stats(const double* Y0, int64_t m, int n, int n_pad, int c, int nk, WeightConsts wc,
                        LikParams lik, const double* grid_dev, double* Yr, double* ell, double* rss,
                        int* best, double* ellmax, double* h2_out, int* bin_count, int* flags,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, TraitFuse* fuse) {
+  if (fuse) fuse->done = false;
   // table form when the block's weight table fits in shared memory (BXD-size grid scans: 20 KB)
   const int KB = 32 / (1 + c);
   const int nbatch = (nk + KB - 1) / KB;
@@ -617,10 +640,16 @@ int launch_trait_stats(const double* Y0, int64_t m, int n, int n_pad, int c, int
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t want = (m + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    TraitFuse f{nullptr, nullptr, nullptr, 0, false};
+    if (fuse && nbatch == 1 && fuse->Top && fuse->e && fuse->et) {
+      f = *fuse;
+      fuse->done = true;
+    }
+    const int64_t cols = f.Top ? f.tcol_pad : m;
+    const int64_t want = (cols + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const unsigned blocks = (unsigned)std::min<int64_t>(want, (int64_t)sms * 4);  // one resident wave
     trait_stats_table_kernel<<<blocks, 32 * WARPS_PER_BLOCK, table_smem, stream>>>(
-        Y0, m, n, n_pad, c, nk, wc, lik, grid_dev, Yr, ell, rss, best, ellmax, h2_out, bin_count, flags);
+        Y0, m, n, n_pad, c, nk, wc, lik, grid_dev, Yr, ell, rss, best, ellmax, h2_out, bin_count, flags, f);
     return 1;
   }
   const size_t smem = (size_t)WARPS_PER_BLOCK * n_pad * sizeof(double);
