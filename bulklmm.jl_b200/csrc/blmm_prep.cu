@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
   const int KB = 32 / (1 + c);  // grid points per batch of 32 lane slots
   const int nbatch = (nk + KB - 1) / KB;
   double* T = smem;                                   // [nbatch][n_pad][32]
-  double* ybase = smem + (size_t)nbatch * n_pad * 32;  // [WARPS_PER_BLOCK][n_pad]
+  double* ybase = smem + (size_t)nbatch * n_pad * 32;  // [WARPS_PER_BLOCK][2][n_pad]: residual and its square
   for (int idx = threadIdx.x; idx < nbatch * n_pad * 32; idx += blockDim.x) {
     const int v = idx & 31, l = (idx >> 5) % n_pad, bt = (idx >> 5) / n_pad;
     const int a = v / KB, k = bt * KB + v % KB;
@@ -369,7 +369,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
   }
   __syncthreads();
   const int a_lane = lane / KB, kk_lane = lane % KB;
-  double* yb = ybase + (int64_t)wid * n_pad;
+  double* yb = ybase + (int64_t)wid * 2 * n_pad;
+  double* yb2 = yb + n_pad;
+  const double* src = (a_lane == 0) ? yb2 : yb;  // this lane's kind: a = 0 sums w y^2, a >= 1 sums (Q sw) y
   const double* sw1 = wc.sw + (int64_t)nk * n_pad;
   const double* Qo = wc.Q + (int64_t)nk * c * n_pad;
   const int64_t jend = fuse.Top ? fuse.tcol_pad : m;
@@ -390,6 +392,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
     for (int l = lane; l < n_pad; l += 32) {
       const double y = proj_elem(yb, sw1, Qo, n_pad, c, l, coef);  // reads only this lane's element of yb
       yb[l] = y;
+      yb2[l] = y * y;
       Yr[j * n_pad + l] = y;
       if (fuse.Top) fuse.Top[((int64_t)(l / KC) * fuse.tcol_pad + j) * KC + (l % KC)] = y;
     }
@@ -402,16 +405,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int l = 0;
       for (; l + 4 <= n; l += 4) {
-        const double y0 = yb[l], y1 = yb[l + 1], y2 = yb[l + 2], y3 = yb[l + 3];
-        s0 = fma(Tb[(l + 0) * 32], a_lane == 0 ? y0 * y0 : y0, s0);
-        s1 = fma(Tb[(l + 1) * 32], a_lane == 0 ? y1 * y1 : y1, s1);
-        s2 = fma(Tb[(l + 2) * 32], a_lane == 0 ? y2 * y2 : y2, s2);
-        s3 = fma(Tb[(l + 3) * 32], a_lane == 0 ? y3 * y3 : y3, s3);
+        s0 = fma(Tb[(l + 0) * 32], src[l + 0], s0);
+        s1 = fma(Tb[(l + 1) * 32], src[l + 1], s1);
+        s2 = fma(Tb[(l + 2) * 32], src[l + 2], s2);
+        s3 = fma(Tb[(l + 3) * 32], src[l + 3], s3);
       }
-      for (; l < n; ++l) {
-        const double y0 = yb[l];
-        s0 = fma(Tb[l * 32], a_lane == 0 ? y0 * y0 : y0, s0);
-      }
+      for (; l < n; ++l) s0 = fma(Tb[l * 32], src[l], s0);
       const double sv = (s0 + s1) + (s2 + s3);
       double rss = sv;
       const double t2 = sv * sv;
@@ -633,7 +632,7 @@ int launch_trait_stats(const double* Y0, int64_t m, int n, int n_pad, int c, int
   // table form when the block's weight table fits in shared memory (BXD-size grid scans: 20 KB)
   const int KB = 32 / (1 + c);
   const int nbatch = (nk + KB - 1) / KB;
-  const size_t table_smem = ((size_t)nbatch * n_pad * 32 + (size_t)WARPS_PER_BLOCK * n_pad) * sizeof(double);
+  const size_t table_smem = ((size_t)nbatch * n_pad * 32 + (size_t)WARPS_PER_BLOCK * 2 * n_pad) * sizeof(double);
   if (table_smem <= 96 * 1024) {
     if (table_smem > 48 * 1024)
       cudaFuncSetAttribute(trait_stats_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_smem);
