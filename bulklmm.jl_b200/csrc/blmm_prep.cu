@@ -496,6 +496,99 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
   }
 }
 
+// Table form of marker_operand_kernel for the weight-folded operand of the grid scans (fold_sw), when the
+// per-block tables fit in shared memory.  As in trait_stats_table_kernel lane v owns one (kind a, grid point k) pair
+// and gets s_k = sum_l w_k g_l^2 and t_ka = sum_l Q_ka sw_k g_l in one pass without cross-lane reductions
+// (||P_k(sw_k g)||^2 = s_k - sum_a t_ka^2; g is first residualised without weights on the covariates, which P_k
+// annihilates anyway, so nothing large cancels).  The second pass writes sw_k P_k(sw_k g) / ||.|| =
+// (w_k g - sum_a (Q_ka sw_k) t_ka) / ||.|| from the same table entries, read through a transposed copy so that
+// lanes walking along l do not collide on one bank.
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
+    marker_operand_table_kernel(const double* __restrict__ G0, int64_t p, int64_t p_pad, int n, int n_pad, int c, int nk,
+                                WeightConsts wc, double* __restrict__ Mop, int* flags) {
+  extern __shared__ double smem[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = 32 / (1 + c);
+  const int nbatch = (nk + KB - 1) / KB;
+  const int nq = n_pad / KC;
+  double* T = smem;                                       // [nbatch][n_pad][32]  (lane-contiguous)
+  double* Tt = T + (size_t)nbatch * n_pad * 32;           // [nbatch][32][n_pad]  (l-contiguous)
+  double* gbase = Tt + (size_t)nbatch * n_pad * 32;       // [WARPS_PER_BLOCK][2][n_pad]
+  for (int idx = threadIdx.x; idx < nbatch * n_pad * 32; idx += blockDim.x) {
+    const int v = idx & 31, l = (idx >> 5) % n_pad, bt = (idx >> 5) / n_pad;
+    const int a = v / KB, k = bt * KB + v % KB;
+    double val = 0.0;
+    if (a <= c && k < nk && l < n) {
+      const double sw = wc.sw[(int64_t)k * n_pad + l];
+      val = (a == 0) ? wc.w[(int64_t)k * n_pad + l] : wc.Q[((int64_t)k * c + (a - 1)) * n_pad + l] * sw;
+    }
+    T[idx] = val;
+    Tt[((size_t)bt * 32 + v) * n_pad + l] = val;
+  }
+  __syncthreads();
+  const int a_lane = lane / KB, kk_lane = lane % KB;
+  double* gb = gbase + (int64_t)wid * 2 * n_pad;
+  double* gb2 = gb + n_pad;
+  const double* src = (a_lane == 0) ? gb2 : gb;
+  const double* sw1 = wc.sw + (int64_t)nk * n_pad;
+  const double* Qo = wc.Q + (int64_t)nk * c * n_pad;
+  for (int64_t i = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wid; i < p_pad; i += (int64_t)gridDim.x * WARPS_PER_BLOCK) {
+    if (i >= p) {
+      for (int k = 0; k < nk; ++k)
+        for (int l = lane; l < n_pad; l += 32) Mop[(((int64_t)k * nq + l / KC) * p_pad + i) * KC + (l % KC)] = 0.0;
+      continue;
+    }
+    for (int l = lane; l < n_pad; l += 32) gb[l] = G0[i * n_pad + l];
+    __syncwarp();
+    double coef[MAXC];
+    proj_coefs(gb, sw1, Qo, n_pad, c, lane, coef);
+    for (int l = lane; l < n_pad; l += 32) {
+      const double gv = proj_elem(gb, sw1, Qo, n_pad, c, l, coef);
+      gb[l] = gv;
+      gb2[l] = gv * gv;
+    }
+    __syncwarp();
+    for (int bt = 0; bt < nbatch; ++bt) {
+      const double* Tb = T + (size_t)bt * n_pad * 32 + lane;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int l = 0;
+      for (; l + 4 <= n; l += 4) {
+        s0 = fma(Tb[(l + 0) * 32], src[l + 0], s0);
+        s1 = fma(Tb[(l + 1) * 32], src[l + 1], s1);
+        s2 = fma(Tb[(l + 2) * 32], src[l + 2], s2);
+        s3 = fma(Tb[(l + 3) * 32], src[l + 3], s3);
+      }
+      for (; l < n; ++l) s0 = fma(Tb[l * 32], src[l], s0);
+      const double sv = (s0 + s1) + (s2 + s3);  // lane (a, kk): a = 0 -> sum w g^2, a >= 1 -> t_a
+      double n2 = sv;
+      const double t2 = sv * sv;
+      for (int a = 1; a <= c; ++a) n2 -= __shfl_sync(0xffffffffu, t2, (a * KB + kk_lane) & 31);
+      const double nrm = sqrt(n2);
+      const bool valid0 = (a_lane == 0) && (bt * KB + kk_lane < nk);
+      if (valid0 && !(nrm > DBL_EPSILON)) atomicExch(&flags[FLAG_ZERO_NORM], 1);
+      const double inv_mine = 1.0 / nrm;  // meaningful in lanes (0, kk)
+      const int kcount = (nk - bt * KB) < KB ? (nk - bt * KB) : KB;
+      const double* Ttb = Tt + (size_t)bt * 32 * n_pad;
+      for (int kk = 0; kk < kcount; ++kk) {
+        const double inv = __shfl_sync(0xffffffffu, inv_mine, kk);
+        double tk[MAXC];
+#pragma unroll
+        for (int a = 0; a < MAXC; ++a)
+          if (a < c) tk[a] = __shfl_sync(0xffffffffu, sv, ((a + 1) * KB + kk) & 31);
+        const int k = bt * KB + kk;
+        for (int l2 = lane; l2 < n_pad; l2 += 32) {
+          double z = Ttb[(size_t)kk * n_pad + l2] * gb[l2];  // w_k g
+#pragma unroll
+          for (int a = 0; a < MAXC; ++a)
+            if (a < c) z = fma(-Ttb[((size_t)(a + 1) * KB + kk) * n_pad + l2], tk[a], z);
+          Mop[(((int64_t)k * nq + l2 / KC) * p_pad + i) * KC + (l2 % KC)] = z * inv;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void alt_scalars_kernel(const double* __restrict__ ell, const double* __restrict__ rss,
                                    const double* __restrict__ ellmax, int64_t m, int64_t tcol_pad, int nk,
                                    double inv_half_n, double* __restrict__ e, double* __restrict__ et) {
@@ -663,6 +756,26 @@ int launch_trait_stats(const double* Y0, int64_t m, int n, int n_pad, int c, int
 
 int launch_marker_operand(const double* G0, int64_t p, int64_t p_pad, int n, int n_pad, int c, int nk,
                           WeightConsts wc, bool fold_sw, double* Mop, int* flags, cudaStream_t stream) {
+  if (fold_sw) {
+    // table form when the block's tables fit in shared memory (BXD-size grid scans: 50 KB)
+    const int KB = 32 / (1 + c);
+    const int nbatch = (nk + KB - 1) / KB;
+    const size_t tsmem = ((size_t)2 * nbatch * n_pad * 32 + (size_t)WARPS_PER_BLOCK * 2 * n_pad) * sizeof(double);
+    if (tsmem <= 56 * 1024) {
+      if (tsmem > 48 * 1024)
+        cudaFuncSetAttribute(marker_operand_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      // one resident wave (4 blocks per SM by shared memory); fewer, longer-lived blocks were measured slower —
+      // the kernel is bound by per-marker latency, not by building the tables
+      const int64_t want = (p_pad + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+      const unsigned blocks = (unsigned)std::min<int64_t>(want, (int64_t)sms * 4);
+      marker_operand_table_kernel<<<blocks, 32 * WARPS_PER_BLOCK, tsmem, stream>>>(G0, p, p_pad, n, n_pad, c, nk, wc, Mop,
+                                                                                    flags);
+      return 1;
+    }
+  }
   const size_t smem = (size_t)WARPS_PER_BLOCK * n_pad * sizeof(double);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(marker_operand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
