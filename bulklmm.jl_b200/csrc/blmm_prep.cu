@@ -41,34 +41,37 @@ struct RotateOps {
   __device__ double b(int k, int64_t col) const { return (col < cols && k < n) ? X[(int64_t)k + col * ldx] : 0.0; }
 };
 
+// RI = output rows per thread: the row tile is 16*RI (64 .. 128), chosen by the launcher so that the padded row
+// count of the result is covered without a mostly-empty second row tile (n_pad = 80 -> RI = 5, one tile).
+template <int RI>
 __global__ void __launch_bounds__(256) rotate_kernel(RotateOps op, double* __restrict__ out, int64_t ldo,
                                                      int64_t ldo_zero) {
-  __shared__ double As[GK][GT + 1];
+  constexpr int RT = 16 * RI;
+  __shared__ double As[GK][RT + 1];
   __shared__ double Bs[GK][GT + 1];
   const int tid = threadIdx.x;
-  const int a0 = blockIdx.y * GT;
+  const int a0 = blockIdx.y * RT;
   const int64_t c0 = (int64_t)blockIdx.x * GT;
   const int tr = tid & 15, tc = tid >> 4;
-  double acc[4][4] = {};
+  double acc[RI][4] = {};
   for (int k0 = 0; k0 < op.n; k0 += GK) {
     {
       const int kk = tid & 15, r = tid >> 4;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        As[kk][r + 16 * i] = op.a(a0 + r + 16 * i, k0 + kk);
-        Bs[kk][r + 16 * i] = op.b(k0 + kk, c0 + r + 16 * i);
-      }
+      for (int i = 0; i < RI; ++i) As[kk][r + 16 * i] = op.a(a0 + r + 16 * i, k0 + kk);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[kk][r + 16 * i] = op.b(k0 + kk, c0 + r + 16 * i);
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      double av[4], bv[4];
+      double av[RI], bv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[kk][tr + 16 * i];
+      for (int i = 0; i < RI; ++i) av[i] = As[kk][tr + 16 * i];
 #pragma unroll
       for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tc * 4 + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
     }
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(256) rotate_kernel(RotateOps op, double* __res
     const int64_t col = c0 + tc * 4 + j;
     if (col >= op.cols) continue;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < RI; ++i) {
       const int row = a0 + tr + 16 * i;
       if (row < ldo_zero) out[(int64_t)row + col * ldo] = (row < op.n) ? acc[i][j] : 0.0;
     }
@@ -692,8 +695,17 @@ int launch_rotate(const double* U, const double* X, int64_t ldx, double* out, in
                   int n, int64_t cols, cudaStream_t stream) {
   if (cols <= 0) return 0;
   RotateOps op{U, X, ldx, n, cols};
-  dim3 grid((unsigned)((cols + GT - 1) / GT), (unsigned)((ldo_zero + GT - 1) / GT));
-  rotate_kernel<<<grid, 256, 0, stream>>>(op, out, ldo, ldo_zero);
+  // row tile: the smallest of 64/80/96/112/128 that covers the padded rows in as few tiles as possible
+  const int64_t tiles128 = (ldo_zero + 127) / 128;
+  const int ri = (int)std::min<int64_t>(8, std::max<int64_t>(4, ((ldo_zero + tiles128 - 1) / tiles128 + 15) / 16));
+  dim3 grid((unsigned)((cols + GT - 1) / GT), (unsigned)((ldo_zero + 16 * ri - 1) / (16 * ri)));
+  switch (ri) {
+    case 4: rotate_kernel<4><<<grid, 256, 0, stream>>>(op, out, ldo, ldo_zero); break;
+    case 5: rotate_kernel<5><<<grid, 256, 0, stream>>>(op, out, ldo, ldo_zero); break;
+    case 6: rotate_kernel<6><<<grid, 256, 0, stream>>>(op, out, ldo, ldo_zero); break;
+    case 7: rotate_kernel<7><<<grid, 256, 0, stream>>>(op, out, ldo, ldo_zero); break;
+    default: rotate_kernel<8><<<grid, 256, 0, stream>>>(op, out, ldo, ldo_zero); break;
+  }
   return 1;
 }
 
