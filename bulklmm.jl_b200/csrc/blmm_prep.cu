@@ -631,9 +631,19 @@ __global__ void bin_scatter_kernel(const int* __restrict__ best, const double* _
                                    const int* __restrict__ bin_start, int* bin_cursor, int* __restrict__ col_map,
                                    double* __restrict__ et) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
+  const bool live = j < m;
+  const unsigned active = __ballot_sync(0xffffffffu, live);
+  if (!live) return;
   const int b = best[j];
-  const int pos = bin_start[b] + atomicAdd(&bin_cursor[b], 1);
+  // one atomic per (warp, bin) instead of one per trait: the lanes of a warp that chose the same grid point
+  // take consecutive slots (there are only |grid| cursors for all m traits)
+  const unsigned peers = __match_any_sync(active, b);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&bin_cursor[b], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  const int pos = bin_start[b] + base + __popc(peers & ((1u << lane) - 1u));
   col_map[pos] = (int)j;
   et[pos] = 1.0 / rss[(int64_t)b * m + j];
 }
