@@ -34,7 +34,7 @@ struct blmm_ctx {
   cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap the scan (host-buffer calls)
   cudaEvent_t chunk_ev[16] = {};
   cudaEvent_t copied_ev[16] = {};      // chunk's index panel has landed in h_idx
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;  // marker-side preprocessing on copy_stream
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, wc_ev = nullptr;  // marker-side preprocessing on copy_stream
   uint8_t* h_idx = nullptr;            // pinned staging of the h2 index panel (host-buffer alt-grid calls)
   size_t h_idx_cap = 0;
   cusolverDnHandle_t solver = nullptr;
@@ -130,7 +130,7 @@ void rotate_markers(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_s
 void rotate_traits(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space);
 
 Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool with_markers,
-                      bool with_traits = true) {
+                      bool with_traits = true, bool covariates_on_second_stream = false) {
   Rotated R;
   R.n = (int)pr->n;
   R.nq = num_kchunks(pr->n);
@@ -151,7 +151,15 @@ Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool
   R.lambda = stage_in(ctx, S_LAM, pr->lambda, n, mem_space);
   const double* dC = stage_in(ctx, S_C_IN, pr->Covar, n * R.c, mem_space);
   R.C0 = ws<double>(ctx, S_C0, (size_t)R.n_pad * R.c);
-  ctx->launches += launch_rotate(dU, dC, pr->n, R.C0, R.n_pad, R.n_pad, R.n, R.c, ctx->stream);
+  cudaStream_t cov_stream = ctx->stream;
+  if (covariates_on_second_stream) {
+    // grid scans: the covariate rotation and everything that hangs off it on the marker side run on the second
+    // stream from here on, while the main stream goes straight to the trait rotation
+    CUDA_TRY(cudaEventRecord(ctx->fork_ev, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
+    cov_stream = ctx->copy_stream;
+  }
+  ctx->launches += launch_rotate(dU, dC, pr->n, R.C0, R.n_pad, R.n_pad, R.n, R.c, cov_stream);
   R.Y0 = nullptr;
   if (with_traits) rotate_traits(ctx, pr, R, mem_space);
   R.G0 = nullptr;
@@ -178,9 +186,11 @@ void rotate_markers(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_s
 // marker chain runs on the second stream while the main stream does the traits.  Returns after queueing;
 // the caller makes the main stream wait on ctx->join_ev before the scan.
 void fork_marker_side(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space, int nk, WeightConsts wc,
-                      bool fold_sw, double* Mop, int64_t p_pad) {
-  CUDA_TRY(cudaEventRecord(ctx->fork_ev, ctx->stream));
-  CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
+                      bool fold_sw, double* Mop, int64_t p_pad, bool already_forked = false) {
+  if (!already_forked) {
+    CUDA_TRY(cudaEventRecord(ctx->fork_ev, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
+  }
   R.p = pr->p;
   rotate_markers(ctx, pr, R, mem_space, ctx->copy_stream);
   ctx->launches += launch_marker_operand(R.G0, R.p, p_pad, R.n, R.n_pad, R.c, nk, wc, fold_sw, Mop, ctx->d_flags,
@@ -279,15 +289,20 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   reset_flags(ctx);
   const double* d_grid = upload_grid(ctx, o);
   // rotation matrix, covariates and weight constants first (both sides need them), then the marker side forks
-  Rotated R = rotate_inputs(ctx, pr, ms, false, false);
-  WeightConsts wc = weight_ws(ctx, nk, R.n_pad, R.c);
-  ctx->launches += launch_weight_consts(d_grid, nk, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags, ctx->stream);
   const int64_t p_pad = round_up(p, SCAN_MT);
-  double* Mop = ws<double>(ctx, S_MOP, (size_t)nk * R.n_pad * p_pad);
-  ws<double>(ctx, S_G_IN, ms == BLMM_MEM_HOST ? (size_t)R.n * p : 1);  // (re)allocations before the fork: cudaFree
-  ws<double>(ctx, S_G0, (size_t)R.n_pad * p);                          // would otherwise synchronise mid-overlap
-  fork_marker_side(ctx, pr, R, ms, nk, wc, true, Mop, p_pad);
+  ws<double>(ctx, S_G_IN, ms == BLMM_MEM_HOST ? (size_t)pr->n * p : 1);  // (re)allocations before the fork: cudaFree
+  ws<double>(ctx, S_G0, (size_t)num_kchunks(pr->n) * KC * p);            // would otherwise synchronise mid-overlap
+  double* Mop = ws<double>(ctx, S_MOP, (size_t)nk * num_kchunks(pr->n) * KC * p_pad);
+  WeightConsts wc = weight_ws(ctx, nk, num_kchunks(pr->n) * KC, (int)pr->c);
+  // second stream: covariate rotation -> weight constants -> marker rotation -> marker operand;
+  // main stream: trait rotation, then (after the weight constants) the trait statistics
+  Rotated R = rotate_inputs(ctx, pr, ms, false, false, true);
+  ctx->launches += launch_weight_consts(d_grid, nk, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags,
+                                        ctx->copy_stream);
+  CUDA_TRY(cudaEventRecord(ctx->wc_ev, ctx->copy_stream));
+  fork_marker_side(ctx, pr, R, ms, nk, wc, true, Mop, p_pad, true);
   rotate_traits(ctx, pr, R, ms);
+  CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->wc_ev, 0));
 
   double* Yr = ws<double>(ctx, S_YR, (size_t)R.n_pad * m);
   double* ell = ws<double>(ctx, S_ELL, (size_t)nk * m);
@@ -977,7 +992,8 @@ int blmm_create(blmm_ctx** out, int device) {
             cudaMallocHost(&ctx->h_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
-       cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) == cudaSuccess;
+       cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&ctx->wc_ev, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < 16; ++i)
     ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->copied_ev[i], cudaEventDisableTiming) == cudaSuccess;
@@ -1003,6 +1019,7 @@ void blmm_destroy(blmm_ctx* ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+  if (ctx->wc_ev) cudaEventDestroy(ctx->wc_ev);
   for (int i = 0; i < 16; ++i) {
     if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     if (ctx->copied_ev[i]) cudaEventDestroy(ctx->copied_ev[i]);
