@@ -76,7 +76,8 @@ __global__ void quantile7_kernel(const double* __restrict__ sorted, int64_t n, c
   const int64_t lo = (int64_t)floor(h);
   const int64_t hi = lo + 1 < n ? lo + 1 : lo;
   const double g = h - (double)lo;
-  out[i] = sorted[lo] + g * (sorted[hi] - sorted[lo]);
+  // a + g (b - a) with separate roundings, as Statistics.jl's quantile evaluates it (no FMA contraction)
+  out[i] = __dadd_rn(sorted[lo], __dmul_rn(g, __dsub_rn(sorted[hi], sorted[lo])));
 }
 
 __global__ void scale_rows_kernel(const double* __restrict__ X, const double* __restrict__ w, int64_t n,

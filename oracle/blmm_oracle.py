@@ -741,11 +741,27 @@ def scan(y, g, K, covar=None, weights=None, prior_variance=0.0, prior_sample_siz
 # ----------------------------------------------------------------------------------------
 # analysis_helpers/single_trait_analysis.jl
 # ----------------------------------------------------------------------------------------
+def quantile_type7(x: np.ndarray, probs) -> np.ndarray:
+    """Julia's `quantile(x, p)` default (alpha = beta = 1, Hyndman-Fan type 7) as Statistics.jl evaluates it:
+    h = (n-1) p, a = x_sorted[floor h], b = the next one, result a + (h - floor h) (b - a), each operation rounded
+    on its own (numpy's `quantile` switches to b - (b-a)(1-t) for t >= 0.5 and can differ in the last bit)."""
+    xs = np.sort(np.asarray(x, dtype=np.float64))
+    n = xs.shape[0]
+    out = []
+    for pr in np.atleast_1d(np.asarray(probs, dtype=np.float64)):
+        h = min(max((n - 1) * float(pr), 0.0), float(n - 1))
+        lo = int(math.floor(h))
+        hi = min(lo + 1, n - 1)
+        g = h - lo
+        out.append(float(xs[lo]) + g * (float(xs[hi]) - float(xs[lo])))
+    return np.array(out)
+
+
 def get_thresholds(L: np.ndarray, signif_level: Sequence[float]):
-    """src/analysis_helpers/single_trait_analysis.jl:13-23 (Julia `quantile` = type 7 = numpy 'linear')."""
+    """src/analysis_helpers/single_trait_analysis.jl:13-23: quantile of the per-permutation maxima at 1 - level."""
     peaks = np.max(L, axis=0)
     probs = 1.0 - np.asarray(signif_level, dtype=np.float64)
-    return {"probs": probs, "thrs": np.quantile(peaks, probs)}
+    return {"probs": probs, "thrs": quantile_type7(peaks, probs)}
 
 
 # ----------------------------------------------------------------------------------------

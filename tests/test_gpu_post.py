@@ -49,7 +49,8 @@ def test_thresholds_type7_quantiles(engine):
         mx = rng.gamma(2.0, 1.0, size=nperms)
         sl = [0.1, 0.05, 0.01, 1.0, 0.0]
         got = thresholds_from_max(mx, sl, engine=engine)
-        assert np.array_equal(got.thrs, np.quantile(mx, 1.0 - np.asarray(sl)))
+        assert np.array_equal(got.thrs, orc.quantile_type7(mx, 1.0 - np.asarray(sl)))  # bit for bit
+        assert np.allclose(got.thrs, np.quantile(mx, 1.0 - np.asarray(sl)), rtol=1e-14, atol=0)
     Lp = rng.gamma(1.0, 1.0, size=(50, 300))
     t = get_thresholds(Lp, [0.1, 0.05], engine=engine)
     tr = orc.get_thresholds(Lp, [0.1, 0.05])
