@@ -15,7 +15,7 @@ MEM_HOST, MEM_DEVICE = 0, 1
 METHOD_NULL_GRID, METHOD_ALT_GRID, METHOD_NULL_EXACT = 0, 1, 2
 H2PANEL_REFERENCE, H2PANEL_ARGMAX = 0, 1
 DECOMP_EIGEN, DECOMP_SVD = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -39,6 +39,8 @@ class Opts(C.Structure):
 SIGNATURES = {
     "blmm_abi_version": (C.c_int, []),
     "blmm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "blmm_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]),
+    "blmm_device_count": (C.c_int, [C.c_void_p]),
     "blmm_destroy": (None, [C.c_void_p]),
     "blmm_last_error": (C.c_char_p, [C.c_void_p]),
     "blmm_sync": (C.c_int, [C.c_void_p]),
@@ -46,6 +48,7 @@ SIGNATURES = {
     "blmm_launch_count": (C.c_int64, [C.c_void_p]),
     "blmm_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "blmm_last_scan_ms": (C.c_double, [C.c_void_p]),
+    "blmm_last_gather_ms": (C.c_double, [C.c_void_p]),
     "blmm_kinship": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]),
     "blmm_decompose": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                  C.POINTER(C.c_int), C.c_int]),

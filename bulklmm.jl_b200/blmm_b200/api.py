@@ -47,17 +47,31 @@ def _ptr(a: Optional[np.ndarray]):
 
 
 class Engine:
-    """One context = one GPU (blmm_create).  Not thread-safe: one call in flight per engine."""
+    """One context = one GPU (blmm_create), or, with `devices=[...]`, several GPUs of one box behind one
+    context (blmm_create_multi: traits / permutation columns sharded inside the library).  Not thread-safe:
+    one call in flight per engine."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices: Optional[Sequence[int]] = None):
         self.lib = L.load()
         h = C.c_void_p()
-        st = self.lib.blmm_create(C.byref(h), int(device))
+        if devices is not None:
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            st = self.lib.blmm_create_multi(C.byref(h), devs, len(devices))
+            device = int(devices[0]) if len(devices) else 0
+        else:
+            st = self.lib.blmm_create(C.byref(h), int(device))
         if st != L.OK:
             raise BlmmError(st, "blmm_create failed: no usable sm_100 (B200) device" if st == L.E_NO_DEVICE
                             else f"blmm_create failed with status {st}")
         self.h = h
         self.device = device
+
+    @property
+    def device_count(self) -> int:
+        return int(self.lib.blmm_device_count(self.h))
+
+    def last_gather_ms(self) -> float:
+        return float(self.lib.blmm_last_gather_ms(self.h))
 
     def close(self):
         if getattr(self, "h", None):
@@ -127,6 +141,10 @@ class Engine:
         n = Covar.shape[0]
         m = 0 if Y is None else Y.shape[1]
         p = 0 if G is None else G.shape[1]
+        # raw pointers cross the ABI next: every array must have the n rows the library will read
+        if (U.ndim != 2 or U.shape != (n, n) or lam.shape != (n,) or (Y is not None and Y.shape[0] != n)
+                or (G is not None and G.shape[0] != n) or (weights is not None and weights.shape != (n,))):
+            raise BlmmError(L.E_DIM, "Dimension mismatch.")
         pr = self.make_problem(n, p, m, Covar.shape[1],
                                None if Y is None else Y.ctypes.data, None if G is None else G.ctypes.data,
                                Covar.ctypes.data, U.ctypes.data, lam.ctypes.data,

@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "blmm_b200", "lib")
 LIB = os.path.join(LIBDIR, "libblmm_b200.so")
-SOURCES = ["blmm_api.cu", "blmm_prep.cu", "blmm_fit.cu", "blmm_scan.cu", "blmm_scan_stream.cu", "blmm_post.cu", "blmm_io.cu"]
+SOURCES = ["blmm_api.cu", "blmm_multi.cu", "blmm_hostpipe.cu", "blmm_prep.cu", "blmm_fit.cu", "blmm_scan.cu",
+           "blmm_scan_stream.cu", "blmm_post.cu", "blmm_io.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-pthread"]
 
@@ -47,7 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if pr.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcusolver", "-lpthread", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcusolver", "-lpthread", "-ldl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         subprocess.run(cmd, check=True)
     return LIB
 

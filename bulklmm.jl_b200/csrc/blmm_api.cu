@@ -9,72 +9,16 @@
 #include <string.h>
 
 #include <algorithm>
-#include <atomic>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../../include/blmm_b200.h"
+#include "blmm_ctx.cuh"
 #include "blmm_kernels.cuh"
 
 using namespace blmm;
 
-// workspace slots (grow-only device buffers owned by the context)
-enum Slot {
-  S_Y_IN, S_G_IN, S_C_IN, S_U_IN, S_LAM, S_GRID, S_Y0, S_C0, S_G0, S_YR, S_W, S_SW, S_Q, S_SLW, S_LDS,
-  S_ELL, S_RSS, S_BEST, S_ELLMAX, S_MOP, S_TOP, S_E, S_ET, S_BINS, S_TILEK0, S_COLMAP, S_L, S_H2P, S_H2V,
-  S_SIG2, S_ELLV, S_Z, S_PERM, S_COLMAX, S_KPART, S_KIN, S_SOLVER, S_EIGV, S_MISC, S_LOGTAB, S_XOP, S_DYINV, S_PVAL, S_OBSW, S_UW, S_SORT, S_SORTTMP, S_PROBS, S_H2IDX, S_UNITCTR,
-  S_COUNT
-};
-
-struct blmm_ctx {
-  int device = 0;
-  int sm_count = 0;
-  cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap the scan (host-buffer calls)
-  cudaEvent_t chunk_ev[16] = {};
-  cudaEvent_t copied_ev[16] = {};      // chunk's index panel has landed in h_idx
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, wc_ev = nullptr;  // marker-side preprocessing on copy_stream
-  uint8_t* h_idx = nullptr;            // pinned staging of the h2 index panel (host-buffer alt-grid calls)
-  size_t h_idx_cap = 0;
-  cusolverDnHandle_t solver = nullptr;
-  void* buf[S_COUNT] = {};
-  size_t cap[S_COUNT] = {};
-  int* d_flags = nullptr;
-  int* h_flags = nullptr;  // pinned
-  std::string err;
-  int64_t launches = 0;
-  int profiling = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool scan_timed = false;
-};
-
 namespace {
-
-struct Fail {
-  int code;
-  std::string msg;
-};
-
-#define CUDA_TRY(expr)                                                                          \
-  do {                                                                                          \
-    cudaError_t _e = (expr);                                                                    \
-    if (_e != cudaSuccess)                                                                      \
-      throw Fail{BLMM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)};              \
-  } while (0)
-
-template <typename T>
-T* ws(blmm_ctx* ctx, Slot s, size_t count) {
-  const size_t bytes = std::max<size_t>(count * sizeof(T), 256);
-  if (ctx->cap[s] < bytes) {
-    if (ctx->buf[s]) CUDA_TRY(cudaFree(ctx->buf[s]));
-    ctx->buf[s] = nullptr;
-    ctx->cap[s] = 0;
-    CUDA_TRY(cudaMalloc(&ctx->buf[s], bytes));
-    ctx->cap[s] = bytes;
-  }
-  return reinterpret_cast<T*>(ctx->buf[s]);
-}
 
 // device view of an input matrix: the caller's pointer (device mode) or a staged copy (host mode)
 const double* stage_in(blmm_ctx* ctx, Slot s, const double* p, size_t count, int mem_space,
@@ -85,19 +29,44 @@ const double* stage_in(blmm_ctx* ctx, Slot s, const double* p, size_t count, int
   return d;
 }
 
-void reset_flags(blmm_ctx* ctx) { CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(int), ctx->stream)); }
-
-// Blocks until the queued work is done and turns raised device flags into the reference's errors.
+// Device status flags are raised by kernels and collected HERE: they are cleared only after they have been read, so
+// that a condition raised by an asynchronous (device-pointer) call is reported by the next blmm_sync or host-buffer
+// call instead of being wiped by the next call's entry.
 void finish_and_check(blmm_ctx* ctx) {
   CUDA_TRY(cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost,
                            ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ctx->d_flags, 0, FLAG_COUNT * sizeof(int), ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   CUDA_TRY(cudaGetLastError());
+  if (ctx->h_flags[FLAG_PERM_RANGE])
+    throw Fail{BLMM_E_INVALID, "perm_idx entries must be 0-based indices in 0..n-1"};
   if (ctx->h_flags[FLAG_WEIGHTS]) throw Fail{BLMM_E_WEIGHTS, "Some weights are not positive."};
   if (ctx->h_flags[FLAG_NOT_SPD])
     throw Fail{BLMM_E_NOT_SPD, "Covariate matrix is rank deficient (weighted Gram matrix not positive definite)."};
   if (ctx->h_flags[FLAG_ZERO_NORM])
     throw Fail{BLMM_E_ZERO_NORM, "Dividing by zeros: the input vector can not contain any zeros!"};
+}
+
+HostPipe* host_pipe(blmm_ctx* ctx) {
+  if (!ctx->pipe) ctx->pipe = hostpipe_create(ctx->device, ctx->host_threads > 0 ? ctx->host_threads : default_host_threads());
+  return ctx->pipe;
+}
+
+// A p x cols result (device, leading dimension p) into the caller's host matrix (leading dimension ld), queued on
+// `stream`: one DMA when the destination is pinned, the bounce ring + drain threads when it is pageable.
+void matrix_to_host(blmm_ctx* ctx, cudaStream_t stream, double* dst, int64_t ld, const double* src_dev, int64_t p,
+                    int64_t cols, bool pinned) {
+  if (!dst || cols <= 0) return;
+  if (pinned)
+    CUDA_TRY(cudaMemcpy2DAsync(dst, ld * sizeof(double), src_dev, p * sizeof(double), p * sizeof(double), cols,
+                               cudaMemcpyDeviceToHost, stream));
+  else
+    hostpipe_push(host_pipe(ctx), stream, dst, ld, src_dev, p, p, cols, nullptr);
+}
+
+// Large pageable results go through the ring; small ones are not worth the hand-over.
+bool via_ring(const double* dst, int64_t p, int64_t cols) {
+  return (double)p * (double)cols * 8.0 >= 8e6 && !host_ptr_is_pinned(dst);
 }
 
 void check_problem(const blmm_problem* pr, bool need_markers, bool need_decomp = true) {
@@ -286,7 +255,6 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   const int64_t ld = o->ld_out ? o->ld_out : p;
   if (ld < p) throw Fail{BLMM_E_INVALID, "ld_out < p"};
   if (m == 0) return BLMM_OK;
-  reset_flags(ctx);
   const double* d_grid = upload_grid(ctx, o);
   // rotation matrix, covariates and weight constants first (both sides need them), then the marker side forks
   const int64_t p_pad = round_up(p, SCAN_MT);
@@ -383,72 +351,32 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   }
   CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));  // marker operand ready
   if (ms == BLMM_MEM_HOST && alt && P.n_tiles_t >= 16 && o->chisq_df <= 0) {
-    // Host-buffer alt-grid: the p x m panels (2 x 2 GB at BXD size) leave over PCIe, which takes ~5x
-    // the scan itself.  Scan the trait tiles in chunks and copy each chunk's columns back on a
-    // second stream while the next chunk is scanned.  The h2 panel holds one of <= 255 grid values per
-    // entry, so it crosses PCIe as one-byte grid indices (1/8 of the bytes) into pinned staging and is
-    // expanded to grid[index] in the caller's Float64 array by host threads while later chunks copy.
+    // Host-buffer alt-grid: the p x m panels (2 x 2 GB at BXD size) leave over PCIe, which takes ~4x the scan
+    // itself.  The trait tiles are scanned in chunks, and each chunk's columns are copied back on the second stream
+    // while the next chunks are scanned.  The h2 panel holds one of <= 255 grid values per entry, so it crosses
+    // PCIe as one-byte grid indices (1/8 of the bytes) through the pinned ring and is expanded to grid[index] in
+    // the caller's Float64 array by the drain threads; L goes straight into a pinned destination, or through the
+    // same ring into a pageable one (blmm_hostpipe.cu).
     const int n_tiles = P.n_tiles_t;
-    // PCIe is the bottleneck, so what matters is how soon the first copy starts and how little expansion is left
-    // after the last one: more, smaller chunks for big panels
-    constexpr int MAX_CHUNK = 16;
+    // PCIe is the bottleneck, so what matters is how soon the first copy starts: more, smaller chunks for big panels
     const int nchunk = n_tiles >= 64 ? MAX_CHUNK : 8;
-    // Worth it when the panel is large (PCIe time saved > host expansion time): >= 1e8 entries by default.
-    // BLMM_B200_H2_TRANSFER = index | f64 overrides; BLMM_B200_HOST_THREADS sets the expansion thread count
-    // (default min(16, cores - 1); several ranks sharing one host should divide the cores between them).
+    // The index encoding is worth it when the panel is large (PCIe time saved > host expansion time): >= 1e8
+    // entries by default.  BLMM_B200_H2_TRANSFER = index | f64 overrides; BLMM_B200_HOST_THREADS sets the drain
+    // thread count (default min(16, cores - 1), divided between the GPUs of a multi-GPU context).
     const char* h2_mode = getenv("BLMM_B200_H2_TRANSFER");
     const bool want_idx = h2_mode ? (h2_mode[0] == 'i') : ((double)p * (double)m >= 1e8);
     const bool idx_panel = dH && want_idx && P.nq <= scan_max_nq(P.nk);
-    uint8_t* dI = nullptr;
-    if (idx_panel) {
-      dI = ws<uint8_t>(ctx, S_H2IDX, (size_t)p * m);
-      if (ctx->h_idx_cap < (size_t)p * m) {
-        if (ctx->h_idx) CUDA_TRY(cudaFreeHost(ctx->h_idx));
-        ctx->h_idx = nullptr;
-        ctx->h_idx_cap = 0;
-        CUDA_TRY(cudaMallocHost(&ctx->h_idx, (size_t)p * m));
-        ctx->h_idx_cap = (size_t)p * m;
-      }
-    }
+    uint8_t* dI = idx_panel ? ws<uint8_t>(ctx, S_H2IDX, (size_t)p * m) : nullptr;
+    const bool L_pinned = host_ptr_is_pinned(L_out);
+    const bool H_pinned = h2_out && host_ptr_is_pinned(h2_out);
+    HostPipe* pipe = (idx_panel || !L_pinned || (dH && !H_pinned)) ? host_pipe(ctx) : nullptr;
     int64_t cbeg[MAX_CHUNK + 1];
     for (int ch = 0; ch <= nchunk; ++ch)
       cbeg[ch] = std::min<int64_t>((int64_t)((int64_t)n_tiles * ch / nchunk) * SCAN_TT, m);
-    // expansion workers: worker w takes its slice of the columns of every chunk as the chunk lands
-    struct Expander {
-      std::vector<std::thread> th;
-      std::atomic<int> ready{0};
-      std::atomic<bool> abort{false};
-      ~Expander() {
-        abort.store(true);
-        for (auto& t : th) t.join();
-      }
-    } ex;
-    if (idx_panel) {
-      const unsigned hc = std::thread::hardware_concurrency();
-      int W = (int)std::max(1u, std::min(16u, hc > 1 ? hc - 1 : 1u));
-      if (const char* ht = getenv("BLMM_B200_HOST_THREADS")) W = std::max(1, std::min(64, atoi(ht)));
-      const uint8_t* hI = ctx->h_idx;
-      const double* grid = o->h2_grid;
-      for (int w = 0; w < W; ++w)
-        ex.th.emplace_back([&ex, w, W, hI, grid, h2_out, p, ld, &cbeg, nchunk]() {
-          for (int ch = 0; ch < nchunk; ++ch) {
-            while (ex.ready.load(std::memory_order_acquire) <= ch) {
-              if (ex.abort.load()) return;
-              std::this_thread::yield();
-            }
-            const int64_t c0 = cbeg[ch], c1 = cbeg[ch + 1];
-            const int64_t a = c0 + (c1 - c0) * w / W, b = c0 + (c1 - c0) * (w + 1) / W;
-            for (int64_t col = a; col < b; ++col) {
-              const uint8_t* src = hI + col * p;
-              double* dst = h2_out + col * ld;
-              for (int64_t i = 0; i < p; ++i) dst[i] = grid[src[i]];
-            }
-          }
-        });
-    }
+    // every chunk's scan is queued first: the copy loop below may block on ring slots
     for (int ch = 0; ch < nchunk; ++ch) {
       const int t0 = (int)((int64_t)n_tiles * ch / nchunk), t1 = (int)((int64_t)n_tiles * (ch + 1) / nchunk);
-      const int64_t c0 = cbeg[ch], c1 = cbeg[ch + 1];
+      const int64_t c0 = cbeg[ch];
       ScanParams Pc = P;
       Pc.Top = P.Top + (int64_t)t0 * SCAN_TT * KC;
       Pc.e = P.e + (int64_t)t0 * SCAN_TT;
@@ -460,44 +388,30 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
       Pc.n_tiles_t = t1 - t0;
       run_scan(ctx, Pc);
       CUDA_TRY(cudaEventRecord(ctx->chunk_ev[ch], ctx->stream));
-      CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[ch], 0));
-      if (idx_panel) {
-        // indices first: their expansion then overlaps the (8x larger) copy of the chunk's LOD columns
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_idx + c0 * p, dI + c0 * p, (size_t)(c1 - c0) * p, cudaMemcpyDeviceToHost,
-                                 ctx->copy_stream));
-        CUDA_TRY(cudaEventRecord(ctx->copied_ev[ch], ctx->copy_stream));
-      }
-      CUDA_TRY(cudaMemcpy2DAsync(L_out + c0 * ld, ld * sizeof(double), dL + c0 * p, p * sizeof(double),
-                                 p * sizeof(double), c1 - c0, cudaMemcpyDeviceToHost, ctx->copy_stream));
-      if (dH && !idx_panel)
-        CUDA_TRY(cudaMemcpy2DAsync(h2_out + c0 * ld, ld * sizeof(double), dH + c0 * p, p * sizeof(double),
-                                   p * sizeof(double), c1 - c0, cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
-    if (idx_panel)
-      for (int ch = 0; ch < nchunk; ++ch) {
-        CUDA_TRY(cudaEventSynchronize(ctx->copied_ev[ch]));
-        ex.ready.store(ch + 1, std::memory_order_release);
-      }
+    for (int ch = 0; ch < nchunk; ++ch) {
+      const int64_t c0 = cbeg[ch], c1 = cbeg[ch + 1];
+      CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[ch], 0));
+      // indices first: their expansion then overlaps the (8x larger) copy of the chunk's LOD columns
+      if (idx_panel) hostpipe_push(pipe, ctx->copy_stream, h2_out + c0 * ld, ld, dI + c0 * p, p, p, c1 - c0, o->h2_grid);
+      matrix_to_host(ctx, ctx->copy_stream, L_out + c0 * ld, ld, dL + c0 * p, p, c1 - c0, L_pinned);
+      if (dH && !idx_panel) matrix_to_host(ctx, ctx->copy_stream, h2_out + c0 * ld, ld, dH + c0 * p, p, c1 - c0, H_pinned);
+    }
     finish_and_check(ctx);
     CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
-    for (auto& t : ex.th) t.join();
-    ex.th.clear();
+    hostpipe_wait(pipe);
     return BLMM_OK;
   }
   run_scan(ctx, P);
   double* dP = pvals_after_scan(ctx, o, dL, p, m, P.ldL);
 
   if (ms == BLMM_MEM_HOST) {
-    CUDA_TRY(cudaMemcpy2DAsync(L_out, ld * sizeof(double), dL, p * sizeof(double), p * sizeof(double), m,
-                               cudaMemcpyDeviceToHost, ctx->stream));
-    if (dP)
-      CUDA_TRY(cudaMemcpy2DAsync(o->log10p_out, ld * sizeof(double), dP, p * sizeof(double), p * sizeof(double), m,
-                                 cudaMemcpyDeviceToHost, ctx->stream));
-    if (dH)
-      CUDA_TRY(cudaMemcpy2DAsync(h2_out, ld * sizeof(double), dH, p * sizeof(double), p * sizeof(double), m,
-                                 cudaMemcpyDeviceToHost, ctx->stream));
+    matrix_to_host(ctx, ctx->stream, L_out, ld, dL, p, m, !via_ring(L_out, p, m));
+    if (dP) matrix_to_host(ctx, ctx->stream, o->log10p_out, ld, dP, p, m, !via_ring(o->log10p_out, p, m));
+    if (dH) matrix_to_host(ctx, ctx->stream, h2_out, ld, dH, p, m, !via_ring(h2_out, p, m));
     if (h2v) copy_out(ctx, h2_out, h2v, m, ms);
     finish_and_check(ctx);
+    hostpipe_wait(ctx->pipe);
   }
   return BLMM_OK;
 }
@@ -508,7 +422,6 @@ int grid_loglik(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, doubl
   const int ms = o->mem_space, nk = o->ngrid;
   const int64_t m = pr->m;
   if (m == 0) return BLMM_OK;
-  reset_flags(ctx);
   const double* d_grid = upload_grid(ctx, o);
   Rotated R = rotate_inputs(ctx, pr, ms, false);
   WeightConsts wc = weight_ws(ctx, nk, R.n_pad, R.c);
@@ -550,7 +463,6 @@ int fit_h2(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, double* h2
   const int64_t m = pr->m;
   if (m == 0) return BLMM_OK;
   if (o->optim_interval < 1) throw Fail{BLMM_E_INVALID, "optim_interval must be >= 1"};
-  reset_flags(ctx);
   Rotated R = rotate_inputs(ctx, pr, ms, false);
   double* Yr = residualised_traits(ctx, R, o);
   const bool dev = ms == BLMM_MEM_DEVICE;
@@ -581,7 +493,6 @@ int bulkscan_exact(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, do
   const int64_t ld = o->ld_out ? o->ld_out : p;
   if (ld < p) throw Fail{BLMM_E_INVALID, "ld_out < p"};
   if (m == 0) return BLMM_OK;
-  reset_flags(ctx);
   Rotated R = rotate_inputs(ctx, pr, ms, true);
   double* Yr = residualised_traits(ctx, R, o);  // also leaves the w = 1 constants in weight slot 0
   double* h2 = (dev && h2_out) ? h2_out : ws<double>(ctx, S_H2V, m);
@@ -637,14 +548,12 @@ int bulkscan_exact(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, do
   CUDA_TRY(cudaGetLastError());
   double* dP = pvals_after_scan(ctx, o, dL, p, m, P.ldL);
   if (!dev) {
-    CUDA_TRY(cudaMemcpy2DAsync(L_out, ld * sizeof(double), dL, p * sizeof(double), p * sizeof(double), m,
-                               cudaMemcpyDeviceToHost, ctx->stream));
-    if (dP)
-      CUDA_TRY(cudaMemcpy2DAsync(o->log10p_out, ld * sizeof(double), dP, p * sizeof(double), p * sizeof(double), m,
-                                 cudaMemcpyDeviceToHost, ctx->stream));
+    matrix_to_host(ctx, ctx->stream, L_out, ld, dL, p, m, !via_ring(L_out, p, m));
+    if (dP) matrix_to_host(ctx, ctx->stream, o->log10p_out, ld, dP, p, m, !via_ring(o->log10p_out, p, m));
     copy_out(ctx, h2_out, h2, m, ms);
     copy_out(ctx, sigma2_out, s2, m, ms);
     finish_and_check(ctx);
+    hostpipe_wait(ctx->pipe);
   }
   return BLMM_OK;
 }
@@ -660,7 +569,6 @@ int scan_alt(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, double* 
   const int ms = o->mem_space;
   const bool dev = ms == BLMM_MEM_DEVICE;
   const int64_t p = pr->p;
-  reset_flags(ctx);
   Rotated R = rotate_inputs(ctx, pr, ms, true);
   double* Yr = residualised_traits(ctx, R, o);
   double* misc = ws<double>(ctx, S_MISC, 8);  // [0] h2_null, [1] sigma2, [2] ell_null
@@ -698,7 +606,6 @@ int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const 
   const int64_t p = pr->p;
   const int64_t ld = o->ld_out ? o->ld_out : p;
   if (ld < p) throw Fail{BLMM_E_INVALID, "ld_out < p"};
-  reset_flags(ctx);
   Rotated R = rotate_inputs(ctx, pr, ms, true);
   double* Yr = residualised_traits(ctx, R, o);
   double* h2 = (dev && h2_out) ? h2_out : ws<double>(ctx, S_H2V, 1);
@@ -730,7 +637,7 @@ int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const 
   }
   double* Top = ws<double>(ctx, S_TOP, (size_t)R.n_pad * tcol_pad);
   double* et1 = ws<double>(ctx, S_ET, tcol_pad);
-  ctx->launches += launch_pack_perms(z, zrss, d_perm, nperms, R.n, R.n_pad, tcol_pad, Top, et1, ctx->stream);
+  ctx->launches += launch_pack_perms(z, zrss, d_perm, nperms, R.n, R.n_pad, tcol_pad, Top, et1, ctx->d_flags, ctx->stream);
 
   ScanParams P{};
   P.Top = Top;
@@ -760,13 +667,12 @@ int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const 
   run_scan(ctx, P);
   if (!dev) {
     copy_out(ctx, lod_out, d_lod, p, ms);
-    if (d_Lp)
-      CUDA_TRY(cudaMemcpy2DAsync(Lperms_out, ld * sizeof(double), d_Lp, p * sizeof(double), p * sizeof(double), nperms,
-                                 cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_Lp) matrix_to_host(ctx, ctx->stream, Lperms_out, ld, d_Lp, p, nperms, !via_ring(Lperms_out, p, nperms));
     if (d_max) copy_out(ctx, maxlod_out, d_max, nperms, ms);
     copy_out(ctx, h2_out, h2, 1, ms);
     copy_out(ctx, sigma2_out, s2, 1, ms);
     finish_and_check(ctx);
+    hostpipe_wait(ctx->pipe);
   }
   return BLMM_OK;
 }
@@ -826,8 +732,11 @@ int decompose(blmm_ctx* ctx, int64_t n, const double* K, int scheme, double* U_o
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   if (hinfo != 0) throw Fail{BLMM_E_CUDA, "syevd did not converge (info = " + std::to_string(hinfo) + ")"};
   if (nneg_out) {
+    // the reference warns on eigen values < -1e-7 (src/transform_helpers.jl:27-30); its svd branch tests the
+    // singular values, which are never negative (:42-45), so it never warns there
     int c = 0;
-    for (int64_t i = 0; i < n; ++i) c += hl[i] < -1e-7;
+    if (scheme == BLMM_DECOMP_EIGEN)
+      for (int64_t i = 0; i < n; ++i) c += hl[i] < -1e-7;
     *nneg_out = c;
   }
   // eigen: ascending eigenvalues (LAPACK order).  svd: singular values |lambda| descending.
@@ -948,8 +857,14 @@ int guarded(blmm_ctx* ctx, F&& f) {
     return f();
   } catch (const Fail& fl) {
     ctx->err = fl.msg;
+    // leave nothing in flight that still writes into the caller's arrays, and no stale device flag
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    try {
+      hostpipe_wait(ctx->pipe);
+    } catch (...) {
+    }
+    if (ctx->d_flags) cudaMemset(ctx->d_flags, 0, FLAG_COUNT * sizeof(int));
     cudaGetLastError();
     return fl.code;
   } catch (const std::exception& ex) {
@@ -989,14 +904,14 @@ int blmm_create(blmm_ctx** out, int device) {
             cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc(&ctx->d_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
+            cudaMemset(ctx->d_flags, 0, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaMallocHost(&ctx->h_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
        cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) == cudaSuccess &&
        cudaEventCreateWithFlags(&ctx->wc_ev, cudaEventDisableTiming) == cudaSuccess;
-  for (int i = 0; ok && i < 16; ++i)
-    ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&ctx->copied_ev[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < MAX_CHUNK; ++i)
+    ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     blmm_destroy(ctx);
     return BLMM_E_CUDA;
@@ -1005,25 +920,50 @@ int blmm_create(blmm_ctx** out, int device) {
   return BLMM_OK;
 }
 
+int blmm_create_multi(blmm_ctx** out, const int* devices, int ndev) {
+  if (!out) return BLMM_E_INVALID;
+  *out = nullptr;
+  if (!devices || ndev < 1 || ndev > 64) return BLMM_E_INVALID;
+  for (int a = 0; a < ndev; ++a)
+    for (int b = a + 1; b < ndev; ++b)
+      if (devices[a] == devices[b]) return BLMM_E_INVALID;
+  if (ndev == 1) return blmm_create(out, devices[0]);
+  blmm_ctx* ctx = new (std::nothrow) blmm_ctx();
+  if (!ctx) return BLMM_E_INVALID;
+  const int st = multi_create(ctx, devices, ndev);
+  if (st != BLMM_OK) {
+    blmm_destroy(ctx);
+    return st;
+  }
+  *out = ctx;
+  return BLMM_OK;
+}
+
+int blmm_device_count(const blmm_ctx* ctx) { return ctx ? multi_ndev(ctx) : 0; }
+
 void blmm_destroy(blmm_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->multi) {
+    multi_destroy(ctx);
+    delete ctx;
+    return;
+  }
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  hostpipe_destroy(ctx->pipe);
   for (int s = 0; s < S_COUNT; ++s)
     if (ctx->buf[s]) cudaFree(ctx->buf[s]);
   if (ctx->d_flags) cudaFree(ctx->d_flags);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
-  if (ctx->h_idx) cudaFreeHost(ctx->h_idx);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
   if (ctx->wc_ev) cudaEventDestroy(ctx->wc_ev);
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < MAX_CHUNK; ++i)
     if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
-    if (ctx->copied_ev[i]) cudaEventDestroy(ctx->copied_ev[i]);
-  }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1032,24 +972,33 @@ void blmm_destroy(blmm_ctx* ctx) {
 const char* blmm_last_error(const blmm_ctx* ctx) { return ctx ? ctx->err.c_str() : "context is NULL"; }
 
 int blmm_sync(blmm_ctx* ctx) {
+  if (ctx && ctx->multi) return multi_sync(ctx);
   return guarded(ctx, [&] {
     finish_and_check(ctx);
     return BLMM_OK;
   });
 }
 
-uint64_t blmm_stream(blmm_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+uint64_t blmm_stream(blmm_ctx* ctx) {
+  if (ctx && ctx->multi) ctx = multi_primary(ctx);
+  return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0;
+}
 
-int64_t blmm_launch_count(const blmm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t blmm_launch_count(const blmm_ctx* ctx) {
+  if (ctx && ctx->multi) return multi_launch_count(ctx);
+  return ctx ? ctx->launches : 0;
+}
 
 int blmm_set_profiling(blmm_ctx* ctx, int on) {
   if (!ctx) return BLMM_E_INVALID;
+  if (ctx->multi) return multi_set_profiling(ctx, on);
   ctx->profiling = on;
   ctx->scan_timed = false;
   return BLMM_OK;
 }
 
 double blmm_last_scan_ms(blmm_ctx* ctx) {
+  if (ctx && ctx->multi) return multi_last_scan_ms(ctx);
   if (!ctx || !ctx->scan_timed) return -1.0;
   float ms = -1.f;
   if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0;
@@ -1057,20 +1006,33 @@ double blmm_last_scan_ms(blmm_ctx* ctx) {
   return (double)ms;
 }
 
+double blmm_last_gather_ms(const blmm_ctx* ctx) { return ctx ? ctx->gather_ms : -1.0; }
+
+// entry points that do not shard run on the primary GPU of a multi-GPU context
+#define PRIMARY(ctx) ((ctx) && (ctx)->multi ? multi_primary(ctx) : (ctx))
+#define FORWARD_ERR(parent, call)                                  \
+  do {                                                             \
+    blmm_ctx* _p = PRIMARY(parent);                                \
+    const int _st = (call);                                        \
+    if ((parent) && _p != (parent)) (parent)->err = _p->err;       \
+    return _st;                                                    \
+  } while (0)
+
 int blmm_kinship(blmm_ctx* ctx, int64_t n, int64_t p, const double* G, double* K_out, int mem_space) {
-  return guarded(ctx, [&] { return kinship(ctx, n, p, G, K_out, mem_space); });
+  FORWARD_ERR(ctx, guarded(_p, [&] { return kinship(_p, n, p, G, K_out, mem_space); }));
 }
 
 int blmm_decompose(blmm_ctx* ctx, int64_t n, const double* K, int scheme, double* U_out, double* lambda_out,
                    int* nneg_out, int mem_space) {
-  return guarded(ctx, [&] { return decompose(ctx, n, K, scheme, U_out, lambda_out, nneg_out, mem_space); });
+  FORWARD_ERR(ctx, guarded(_p, [&] { return decompose(_p, n, K, scheme, U_out, lambda_out, nneg_out, mem_space); }));
 }
 
 int blmm_rotate(blmm_ctx* ctx, const blmm_problem* prob, double* Y0_out, double* X0_out, int mem_space) {
-  return guarded(ctx, [&] { return rotate(ctx, prob, Y0_out, X0_out, mem_space); });
+  FORWARD_ERR(ctx, guarded(_p, [&] { return rotate(_p, prob, Y0_out, X0_out, mem_space); }));
 }
 
 int blmm_bulkscan(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* L_out, double* h2_out) {
+  if (ctx && ctx->multi) return multi_bulkscan(ctx, prob, opts, L_out, h2_out);
   return guarded(ctx, [&] {
     if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
     switch (opts->method) {
@@ -1086,6 +1048,7 @@ int blmm_bulkscan(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts
 }
 
 int blmm_grid_loglik(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* ell_out) {
+  if (ctx && ctx->multi) return multi_grid_loglik(ctx, prob, opts, ell_out);
   return guarded(ctx, [&] {
     if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
     return grid_loglik(ctx, prob, opts, ell_out);
@@ -1094,6 +1057,7 @@ int blmm_grid_loglik(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* o
 
 int blmm_fit_h2(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* h2_out, double* sigma2_out,
                 double* ell_out) {
+  if (ctx && ctx->multi) return multi_fit_h2(ctx, prob, opts, h2_out, sigma2_out, ell_out);
   return guarded(ctx, [&] {
     if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
     return fit_h2(ctx, prob, opts, h2_out, sigma2_out, ell_out);
@@ -1103,6 +1067,8 @@ int blmm_fit_h2(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, 
 int blmm_scan_perms(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, const int32_t* perm_idx,
                     int64_t nperms, double* lod_out, double* Lperms_out, double* maxlod_out, double* sigma2_out,
                     double* h2_out) {
+  if (ctx && ctx->multi)
+    return multi_scan_perms(ctx, prob, opts, perm_idx, nperms, lod_out, Lperms_out, maxlod_out, sigma2_out, h2_out);
   return guarded(ctx, [&] {
     if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
     return scan_perms(ctx, prob, opts, perm_idx, nperms, lod_out, Lperms_out, maxlod_out, sigma2_out, h2_out);
@@ -1111,6 +1077,7 @@ int blmm_scan_perms(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* op
 
 int blmm_scan_null(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* lod_out,
                    double* sigma2_out, double* h2_out) {
+  if (ctx && ctx->multi) return multi_scan_null(ctx, prob, opts, lod_out, sigma2_out, h2_out);
   return guarded(ctx, [&] {
     if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
     return bulkscan_exact(ctx, prob, opts, lod_out, h2_out, sigma2_out);
@@ -1119,24 +1086,24 @@ int blmm_scan_null(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opt
 
 int blmm_scan_alt(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opts* opts, double* lod_out,
                   double* h2_each_marker_out, double* sigma2_out, double* h2_out) {
-  return guarded(ctx, [&] {
+  FORWARD_ERR(ctx, guarded(_p, [&] {
     if (!opts) throw Fail{BLMM_E_INVALID, "opts is NULL"};
-    return scan_alt(ctx, prob, opts, lod_out, h2_each_marker_out, sigma2_out, h2_out);
-  });
+    return scan_alt(_p, prob, opts, lod_out, h2_each_marker_out, sigma2_out, h2_out);
+  }));
 }
 
 int blmm_lod2log10p(blmm_ctx* ctx, const double* lod, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, int df,
                     double* out, int mem_space) {
-  return guarded(ctx, [&] { return lod2log10p(ctx, lod, rows, cols, ld_in, ld_out, df, out, mem_space); });
+  FORWARD_ERR(ctx, guarded(_p, [&] { return lod2log10p(_p, lod, rows, cols, ld_in, ld_out, df, out, mem_space); }));
 }
 
 int blmm_thresholds(blmm_ctx* ctx, const double* maxlod, int64_t nperms, const double* signif_level, int nlev,
                     double* thrs_out, int mem_space) {
-  return guarded(ctx, [&] { return thresholds(ctx, maxlod, nperms, signif_level, nlev, thrs_out, mem_space); });
+  FORWARD_ERR(ctx, guarded(_p, [&] { return thresholds(_p, maxlod, nperms, signif_level, nlev, thrs_out, mem_space); }));
 }
 
 int blmm_weight_kinship(blmm_ctx* ctx, int64_t n, const double* K, const double* w, double* K_out, int mem_space) {
-  return guarded(ctx, [&] { return weight_kinship(ctx, n, K, w, K_out, mem_space); });
+  FORWARD_ERR(ctx, guarded(_p, [&] { return weight_kinship(_p, n, K, w, K_out, mem_space); }));
 }
 
 }  // extern "C"

@@ -19,7 +19,7 @@ constexpr int MAXC = 8;      // covariate columns incl. intercept handled by the
 constexpr int NTRI = MAXC * (MAXC + 1) / 2;
 
 // device-side status flags (one int each), raised by kernels, read back by the host API
-enum Flag { FLAG_WEIGHTS = 0, FLAG_NOT_SPD = 1, FLAG_ZERO_NORM = 2, FLAG_COUNT = 8 };
+enum Flag { FLAG_WEIGHTS = 0, FLAG_NOT_SPD = 1, FLAG_ZERO_NORM = 2, FLAG_PERM_RANGE = 3, FLAG_COUNT = 8 };
 
 __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 __host__ __device__ inline int num_kchunks(int64_t n) { return (int)((n + KC - 1) / KC); }

@@ -93,9 +93,10 @@ int launch_pack_traits(const double* Yr, const int* col_map, int64_t m, int64_t 
 // Permutation operand (transform_permute + column normalisation, src/transform_helpers.jl:94-102,
 // src/scan.jl:531-536): column 0 = z/||z||, column s>=1 = z[perm_idx[:,s-1]]/||z||, where z is the
 // weighted null residual (padded column 0 of Zr) and rss = ||z||^2.
-// Also fills et[0..tcol_pad) with 1 (the columns are already normalised).
+// Also fills et[0..tcol_pad) with 1 (the columns are already normalised).  An index outside 0..n-1 raises
+// FLAG_PERM_RANGE (the entry is not read).
 int launch_pack_perms(const double* z, const double* rss, const int32_t* perm_idx, int64_t nperms, int n,
-                      int n_pad, int64_t tcol_pad, double* Top, double* et, cudaStream_t stream);
+                      int n_pad, int64_t tcol_pad, double* Top, double* et, int* flags, cudaStream_t stream);
 
 // z = P (sw .* y): the re-weighted null residual `copy_r0` of transform_reweight
 // (src/transform_helpers.jl:71-82) for one trait, weight slot 0 of wc.  Writes z (n_pad) and rss.

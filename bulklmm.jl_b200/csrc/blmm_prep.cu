@@ -664,7 +664,8 @@ __global__ void pack_traits_kernel(const double* __restrict__ Yr, const int* __r
 
 __global__ void pack_perms_kernel(const double* __restrict__ z, const double* __restrict__ rss,
                                   const int32_t* __restrict__ perm_idx, int64_t nperms, int n, int64_t tcol_pad,
-                                  int64_t total, double* __restrict__ Top, double* __restrict__ et) {
+                                  int64_t total, double* __restrict__ Top, double* __restrict__ et,
+                                  int* __restrict__ flags) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int kk = (int)(idx % KC);
@@ -673,7 +674,11 @@ __global__ void pack_perms_kernel(const double* __restrict__ z, const double* __
   const int l = q * KC + kk;
   double v = 0.0;
   if (s <= nperms && l < n) {
-    const int src = (s == 0) ? l : perm_idx[(int64_t)l + (s - 1) * n];
+    int src = (s == 0) ? l : perm_idx[(int64_t)l + (s - 1) * n];
+    if ((unsigned)src >= (unsigned)n) {  // not a 0-based index into 1:n (e.g. Julia's 1-based n): refuse, do not read
+      flags[FLAG_PERM_RANGE] = 1;
+      src = 0;
+    }
     v = z[src] / sqrt(*rss);
   }
   Top[idx] = v;
@@ -835,10 +840,10 @@ int launch_pack_traits(const double* Yr, const int* col_map, int64_t m, int64_t 
 }
 
 int launch_pack_perms(const double* z, const double* rss, const int32_t* perm_idx, int64_t nperms, int n,
-                      int n_pad, int64_t tcol_pad, double* Top, double* et, cudaStream_t stream) {
+                      int n_pad, int64_t tcol_pad, double* Top, double* et, int* flags, cudaStream_t stream) {
   const int64_t total = (int64_t)n_pad * tcol_pad;
   pack_perms_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(z, rss, perm_idx, nperms, n, tcol_pad,
-                                                                          total, Top, et);
+                                                                          total, Top, et, flags);
   return 1;
 }
 

@@ -11,11 +11,15 @@
  * Conventions
  *   - return value 0 = success; non-zero = BLMM_E_*; blmm_last_error(ctx) gives the message
  *     (for the conditions the reference itself reports, its exact error string).
- *   - one context = one GPU; one call in flight per context; several contexts may coexist
- *     (multi-GPU = one process or context per GPU, traits / permutations sharded by the host,
- *     see DESIGN.md "Multi-GPU").
+ *   - one context = one GPU (blmm_create) or several GPUs of one box (blmm_create_multi); one call in
+ *     flight per context; several contexts may coexist.  A multi-GPU context shards traits (bulkscan) or
+ *     permutation columns (scan) over its GPUs inside the library — the analogue of the reference's `nb`
+ *     trait blocks, src/bulkscan.jl:263-309 — and returns results bit-identical to a one-GPU context.
  *   - `mem_space` selects whether the data pointers of a call are host or device pointers.
- *     Device-pointer calls are asynchronous on the context's stream until blmm_sync().
+ *     Device-pointer calls are asynchronous on the context's stream until blmm_sync().  On a multi-GPU
+ *     context device pointers live on the PRIMARY GPU (devices[0]); NCCL moves the shards (see below).
+ *   - host results may be ordinary pageable arrays (a Julia Array, a numpy array): large results are staged
+ *     through a pinned ring and moved by host threads; pinned (cudaHostRegister-ed) arrays are written by DMA.
  *   - no C++ exception crosses the boundary; no torch / CUDA types appear in a signature.
  */
 #ifndef BLMM_B200_H
@@ -27,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BLMM_ABI_VERSION 2
+#define BLMM_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define BLMM_API __attribute__((visibility("default")))
@@ -110,6 +114,21 @@ typedef struct {
 /* ---- context ------------------------------------------------------------------------------ */
 BLMM_API int blmm_abi_version(void);
 BLMM_API int blmm_create(blmm_ctx** out, int device);
+/* One context over `ndev` distinct GPUs of this box (ndev == 1 is blmm_create).  Replaces the `nb` keyword's trait
+ * blocks (Threads.@threads, src/bulkscan.jl:263-309) by one host thread + GPU per block:
+ *   blmm_bulkscan, blmm_scan_null, blmm_fit_h2, blmm_grid_loglik   shard the m traits,
+ *   blmm_scan_perms                                                shards the permutation columns,
+ * into contiguous column blocks (cut at the kernel's 128-column tile); G, Covar, U, lambda are replicated.
+ *   BLMM_MEM_HOST  : every GPU reads its block of the caller's arrays and writes its slab of the caller's
+ *                    column-major results over its own PCIe link; no collective.
+ *   BLMM_MEM_DEVICE: (blmm_bulkscan, blmm_scan_perms) the pointers are memory of devices[0]; NCCL over NVLink
+ *                    broadcasts the replicated inputs, scatters the column blocks and gathers the result slabs
+ *                    (LOD, h2 panel / h2_null_list, per-permutation max LOD) into the primary's output arrays;
+ *                    needs ld_out == p.  libnccl.so.2 is loaded at the first such call.
+ * Every other entry point runs on devices[0].                                                          */
+BLMM_API int blmm_create_multi(blmm_ctx** out, const int* devices, int ndev);
+/* Number of GPUs behind the context (1 for blmm_create). */
+BLMM_API int blmm_device_count(const blmm_ctx* ctx);
 BLMM_API void blmm_destroy(blmm_ctx* ctx);
 BLMM_API const char* blmm_last_error(const blmm_ctx* ctx);
 /* Wait for all work queued on the context's stream. */
@@ -124,6 +143,9 @@ BLMM_API int64_t blmm_launch_count(const blmm_ctx* ctx);
  * for the launch and returns its duration in milliseconds (-1 if none was timed).              */
 BLMM_API int blmm_set_profiling(blmm_ctx* ctx, int on);
 BLMM_API double blmm_last_scan_ms(blmm_ctx* ctx);
+/* Multi-GPU device-resident calls: device time (ms, CUDA events on the primary's stream) of the NCCL gather of the
+ * last call, from the end of the primary's own scan to the last slab received; valid after blmm_sync(); -1 if none. */
+BLMM_API double blmm_last_gather_ms(const blmm_ctx* ctx);
 
 /* ---- setup -------------------------------------------------------------------------------- */
 /* calcKinship(geno), src/kinship.jl:4-14.  G: n x p.  K_out: n x n. */
@@ -160,7 +182,8 @@ BLMM_API int blmm_fit_h2(blmm_ctx* ctx, const blmm_problem* prob, const blmm_opt
 
 /* scan(y,g,covar,K; permutation_test=true), src/scan.jl:485-557 (scan_perms_lite).  prob->m must
  * be 1.  perm_idx: n x nperms int32, column-major, 0-based — column s is the shuffle
- * r0[perm_idx[:,s]] the shim drew with the reference's RNG (src/transform_helpers.jl:94-102).
+ * r0[perm_idx[:,s]] the shim drew with the reference's RNG (src/transform_helpers.jl:94-102); an entry outside
+ * 0..n-1 (e.g. Julia's 1-based n) is refused with BLMM_E_INVALID.
  *   lod_out      : p            LODs of the un-permuted trait
  *   Lperms_out   : p x nperms   (ld = opts->ld_out or p), or NULL to skip materialising it
  *   maxlod_out   : nperms       per-permutation max LOD (what get_thresholds consumes,

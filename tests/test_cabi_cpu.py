@@ -18,7 +18,8 @@ def test_header_declares_expected_surface():
     syms = declared_symbols()
     for must in ("blmm_create", "blmm_destroy", "blmm_last_error", "blmm_kinship", "blmm_decompose", "blmm_rotate",
                  "blmm_bulkscan", "blmm_grid_loglik", "blmm_fit_h2", "blmm_scan_perms", "blmm_scan_null",
-                 "blmm_lod2log10p", "blmm_thresholds", "blmm_weight_kinship"):
+                 "blmm_lod2log10p", "blmm_thresholds", "blmm_weight_kinship", "blmm_create_multi",
+                 "blmm_device_count", "blmm_last_gather_ms"):
         assert must in syms
 
 
@@ -28,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/blmm_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.blmm_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.blmm_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_no_cpu_fallback():
