@@ -49,6 +49,7 @@ SIGNATURES = {
     "blmm_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "blmm_last_scan_ms": (C.c_double, [C.c_void_p]),
     "blmm_last_gather_ms": (C.c_double, [C.c_void_p]),
+    "blmm_host_write_gbs": (C.c_double, [C.c_int, C.c_int64]),
     "blmm_kinship": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]),
     "blmm_decompose": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                  C.POINTER(C.c_int), C.c_int]),

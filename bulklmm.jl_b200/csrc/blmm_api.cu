@@ -1008,6 +1008,11 @@ double blmm_last_scan_ms(blmm_ctx* ctx) {
 
 double blmm_last_gather_ms(const blmm_ctx* ctx) { return ctx ? ctx->gather_ms : -1.0; }
 
+double blmm_host_write_gbs(int nthreads, int64_t bytes) {
+  if (bytes < 4096) return -1.0;
+  return host_write_gbs(nthreads > 0 ? nthreads : default_host_threads(), (size_t)bytes);
+}
+
 // entry points that do not shard run on the primary GPU of a multi-GPU context
 #define PRIMARY(ctx) ((ctx) && (ctx)->multi ? multi_primary(ctx) : (ctx))
 #define FORWARD_ERR(parent, call)                                  \

@@ -101,6 +101,8 @@ void hostpipe_push(HostPipe* hp, cudaStream_t stream, double* dst, int64_t ld_ds
 // Blocks until every queued piece is in the caller's arrays; throws Fail on a CUDA error.
 void hostpipe_wait(HostPipe* hp);
 
+double host_write_gbs(int nthreads, size_t bytes);
+
 // ---- blmm_multi.cu ----------------------------------------------------------------------------------------
 int multi_create(blmm_ctx* parent, const int* devices, int ndev);
 void multi_destroy(blmm_ctx* parent);

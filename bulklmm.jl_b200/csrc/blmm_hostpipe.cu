@@ -10,6 +10,7 @@
 #include <emmintrin.h>
 #include <string.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -225,6 +226,33 @@ void hostpipe_wait(HostPipe* hp) {
     hp->error.clear();
     throw Fail{BLMM_E_CUDA, e};
   }
+}
+
+// Streaming-store bandwidth of `nthreads` host threads into a pageable buffer of `bytes` (touched first, best of 3):
+// the rate at which this host can take Float64 results at all — the ceiling of every host-buffer call next to PCIe.
+double host_write_gbs(int nthreads, size_t bytes) {
+  nthreads = std::max(1, std::min(nthreads, 256));
+  const int64_t n = (int64_t)(bytes / 8);
+  double* buf = static_cast<double*>(aligned_alloc(64, (size_t)n * 8));
+  if (!buf) return -1.0;
+  memset(buf, 0, (size_t)n * 8);
+  std::vector<double> src(4096, 1.0);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+      th.emplace_back([&, t] {
+        const int64_t a = n * t / nthreads, b = n * (t + 1) / nthreads;
+        for (int64_t c = a; c < b; c += 4096) copy_nt(buf + c, src.data(), std::min<int64_t>(4096, b - c));
+        _mm_sfence();
+      });
+    for (auto& x : th) x.join();
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    best = std::max(best, (double)n * 8 / sec / 1e9);
+  }
+  free(buf);
+  return best;
 }
 
 }  // namespace blmm

@@ -146,6 +146,10 @@ BLMM_API double blmm_last_scan_ms(blmm_ctx* ctx);
 /* Multi-GPU device-resident calls: device time (ms, CUDA events on the primary's stream) of the NCCL gather of the
  * last call, from the end of the primary's own scan to the last slab received; valid after blmm_sync(); -1 if none. */
 BLMM_API double blmm_last_gather_ms(const blmm_ctx* ctx);
+/* Measurement aid (needs no context, no GPU): GB/s at which `nthreads` host threads (0 = the library's default drain
+ * thread count) fill a `bytes`-sized pageable buffer with streaming stores — the rate at which this host can take
+ * Float64 results at all, i.e. the ceiling of host-buffer calls next to the PCIe rate (bench.py reports both). */
+BLMM_API double blmm_host_write_gbs(int nthreads, int64_t bytes);
 
 /* ---- setup -------------------------------------------------------------------------------- */
 /* calcKinship(geno), src/kinship.jl:4-14.  G: n x p.  K_out: n x n. */
