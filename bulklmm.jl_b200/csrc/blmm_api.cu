@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -57,7 +58,9 @@ HostPipe* host_pipe(blmm_ctx* ctx) {
 void matrix_to_host(blmm_ctx* ctx, cudaStream_t stream, double* dst, int64_t ld, const double* src_dev, int64_t p,
                     int64_t cols, bool pinned) {
   if (!dst || cols <= 0) return;
-  if (pinned)
+  if (pinned && ld == p)
+    CUDA_TRY(cudaMemcpyAsync(dst, src_dev, (size_t)p * cols * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  else if (pinned)
     CUDA_TRY(cudaMemcpy2DAsync(dst, ld * sizeof(double), src_dev, p * sizeof(double), p * sizeof(double), cols,
                                cudaMemcpyDeviceToHost, stream));
   else
@@ -245,7 +248,12 @@ void run_scan(blmm_ctx* ctx, ScanParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
+double trace_now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, double* L_out, double* h2_out) {
+  const double t_enter = trace_now();
   check_problem(pr, true);
   if (!L_out) throw Fail{BLMM_E_INVALID, "L_out is NULL"};
   const bool alt = o->method == BLMM_METHOD_ALT_GRID;
@@ -367,6 +375,15 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     const bool want_idx = h2_mode ? (h2_mode[0] == 'i') : ((double)p * (double)m >= 1e8);
     const bool idx_panel = dH && want_idx && P.nq <= scan_max_nq(P.nk);
     uint8_t* dI = idx_panel ? ws<uint8_t>(ctx, S_H2IDX, (size_t)p * m) : nullptr;
+    if (idx_panel && ctx->h_idx_cap < (size_t)p * m) {
+      // the whole index panel has its own pinned staging (1 byte per entry), so that queueing its copies never
+      // waits for a ring slot: every copy of the call is in the stream before the first one has finished
+      if (ctx->h_idx) CUDA_TRY(cudaFreeHost(ctx->h_idx));
+      ctx->h_idx = nullptr;
+      ctx->h_idx_cap = 0;
+      CUDA_TRY(cudaMallocHost(&ctx->h_idx, (size_t)p * m));
+      ctx->h_idx_cap = (size_t)p * m;
+    }
     const bool L_pinned = host_ptr_is_pinned(L_out);
     const bool H_pinned = h2_out && host_ptr_is_pinned(h2_out);
     HostPipe* pipe = (idx_panel || !L_pinned || (dH && !H_pinned)) ? host_pipe(ctx) : nullptr;
@@ -393,13 +410,25 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
       const int64_t c0 = cbeg[ch], c1 = cbeg[ch + 1];
       CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[ch], 0));
       // indices first: their expansion then overlaps the (8x larger) copy of the chunk's LOD columns
-      if (idx_panel) hostpipe_push(pipe, ctx->copy_stream, h2_out + c0 * ld, ld, dI + c0 * p, p, p, c1 - c0, o->h2_grid);
+      if (idx_panel) {
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_idx + c0 * p, dI + c0 * p, (size_t)(c1 - c0) * p, cudaMemcpyDeviceToHost,
+                                 ctx->copy_stream));
+        CUDA_TRY(cudaEventRecord(ctx->idx_ev[ch], ctx->copy_stream));
+        hostpipe_push_staged(pipe, ctx->idx_ev[ch], h2_out + c0 * ld, ld, ctx->h_idx + c0 * p, p, c1 - c0, o->h2_grid);
+      }
       matrix_to_host(ctx, ctx->copy_stream, L_out + c0 * ld, ld, dL + c0 * p, p, c1 - c0, L_pinned);
       if (dH && !idx_panel) matrix_to_host(ctx, ctx->copy_stream, h2_out + c0 * ld, ld, dH + c0 * p, p, c1 - c0, H_pinned);
     }
+    const double t_queued = trace_now();
     finish_and_check(ctx);
+    const double t_scanned = trace_now();
     CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+    const double t_copied = trace_now();
     hostpipe_wait(pipe);
+    if (getenv("BLMM_B200_TRACE"))
+      fprintf(stderr, "[blmm trace] dev %d alt-grid host call: queued %.2f ms, scans done %.2f, copies done %.2f, drained %.2f\n",
+              ctx->device, (t_queued - t_enter) * 1e3, (t_scanned - t_enter) * 1e3, (t_copied - t_enter) * 1e3,
+              (trace_now() - t_enter) * 1e3);
     return BLMM_OK;
   }
   run_scan(ctx, P);
@@ -911,7 +940,8 @@ int blmm_create(blmm_ctx** out, int device) {
        cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) == cudaSuccess &&
        cudaEventCreateWithFlags(&ctx->wc_ev, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < MAX_CHUNK; ++i)
-    ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->idx_ev[i], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
   if (!ok) {
     blmm_destroy(ctx);
     return BLMM_E_CUDA;
@@ -962,8 +992,11 @@ void blmm_destroy(blmm_ctx* ctx) {
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
   if (ctx->wc_ev) cudaEventDestroy(ctx->wc_ev);
-  for (int i = 0; i < MAX_CHUNK; ++i)
+  for (int i = 0; i < MAX_CHUNK; ++i) {
     if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
+    if (ctx->idx_ev[i]) cudaEventDestroy(ctx->idx_ev[i]);
+  }
+  if (ctx->h_idx) cudaFreeHost(ctx->h_idx);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -48,6 +48,9 @@ struct blmm_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap the scan (host-buffer calls)
   cudaEvent_t chunk_ev[blmm::MAX_CHUNK] = {};
+  cudaEvent_t idx_ev[blmm::MAX_CHUNK] = {};  // chunk's h2 index panel has landed in h_idx
+  uint8_t* h_idx = nullptr;                   // pinned staging of the h2 index panel (host-buffer alt-grid calls)
+  size_t h_idx_cap = 0;
   cudaEvent_t fork_ev = nullptr, join_ev = nullptr, wc_ev = nullptr;  // marker-side preprocessing on copy_stream
   cusolverDnHandle_t solver = nullptr;
   void* buf[blmm::S_COUNT] = {};
@@ -98,6 +101,10 @@ void hostpipe_destroy(HostPipe* hp);
 // call order (the caller orders `stream` after the producer); returns when everything is issued, not when it landed.
 void hostpipe_push(HostPipe* hp, cudaStream_t stream, double* dst, int64_t ld_dst, const void* src_dev, int64_t ld_src,
                    int64_t rows, int64_t cols, const double* grid);
+// The same for a piece the caller has already copied (asynchronously) into its own pinned staging at `staged`
+// (`rows` x `cols`, packed) and marked with `ev`: nothing blocks, the drain threads pick it up when `ev` completes.
+void hostpipe_push_staged(HostPipe* hp, cudaEvent_t ev, double* dst, int64_t ld_dst, const void* staged, int64_t rows,
+                          int64_t cols, const double* grid);
 // Blocks until every queued piece is in the caller's arrays; throws Fail on a CUDA error.
 void hostpipe_wait(HostPipe* hp);
 

@@ -28,7 +28,9 @@ constexpr size_t SLOT_BYTES_INDEX = 1u << 20;  // index pieces expand 8x: 1 MB o
 constexpr int NSLOTS = 24;
 
 struct Task {
-  int slot;
+  int slot;            // ring slot to release afterwards, or -1: the piece sits in caller-owned pinned staging
+  const uint8_t* src;  // where the piece lands on the host (ring slot or staging)
+  cudaEvent_t ev;      // recorded after the device-to-host copy that fills `src`
   double* dst;       // first destination element
   int64_t ld_dst;    // doubles between destination columns
   int64_t rows;      // elements per column in this piece
@@ -100,9 +102,9 @@ struct HostPipe {
         t = tasks.front();
         tasks.pop_front();
       }
-      const cudaError_t e = cudaEventSynchronize(ev[t.slot]);
+      const cudaError_t e = cudaEventSynchronize(t.ev);
       if (e == cudaSuccess) {
-        const uint8_t* src = ring + (size_t)t.slot * SLOT_BYTES;
+        const uint8_t* src = t.src;
         for (int64_t c = 0; c < t.cols; ++c) {
           if (t.grid)
             expand_nt(t.dst + c * t.ld_dst, src + c * t.rows, t.rows, t.grid);
@@ -114,7 +116,7 @@ struct HostPipe {
       {
         std::lock_guard<std::mutex> lk(mu);
         if (e != cudaSuccess && error.empty()) error = std::string("device-to-host copy: ") + cudaGetErrorString(e);
-        free_slots.push_back(t.slot);
+        if (t.slot >= 0) free_slots.push_back(t.slot);
         --pending;
       }
       cv_slot.notify_one();
@@ -147,7 +149,9 @@ HostPipe* hostpipe_create(int device, int nthreads) {
     throw Fail{BLMM_E_CUDA, "cudaMallocHost of the host result ring failed"};
   }
   for (int i = 0; i < NSLOTS; ++i) {
-    if (cudaEventCreateWithFlags(&hp->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+    // blocking sync: a drain thread waiting for its DMA sleeps instead of spinning on a core another drain thread
+    // (or another GPU's) could be copying with
+    if (cudaEventCreateWithFlags(&hp->ev[i], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
       hostpipe_destroy(hp);
       throw Fail{BLMM_E_CUDA, "cudaEventCreate failed"};
     }
@@ -210,11 +214,29 @@ void hostpipe_push(HostPipe* hp, cudaStream_t stream, double* dst, int64_t ld_ds
       }
       {
         std::lock_guard<std::mutex> lk(hp->mu);
-        hp->tasks.push_back(Task{slot, dst + c0 * ld_dst + r0, ld_dst, nr, nc, grid});
+        hp->tasks.push_back(Task{slot, s, hp->ev[slot], dst + c0 * ld_dst + r0, ld_dst, nr, nc, grid});
       }
       hp->cv_task.notify_one();
     }
   }
+}
+
+void hostpipe_push_staged(HostPipe* hp, cudaEvent_t ev, double* dst, int64_t ld_dst, const void* staged, int64_t rows,
+                          int64_t cols, const double* grid) {
+  if (rows <= 0 || cols <= 0) return;
+  const size_t elem = grid ? 1 : 8;
+  // pieces of ~4 MB of destination stores each, so that every drain thread gets a share of every chunk
+  const int64_t cols_per_piece = std::max<int64_t>(1, (int64_t)((4u << 20) / (rows * 8)));
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(staged);
+  {
+    std::lock_guard<std::mutex> lk(hp->mu);
+    for (int64_t c0 = 0; c0 < cols; c0 += cols_per_piece) {
+      const int64_t nc = std::min(cols_per_piece, cols - c0);
+      hp->tasks.push_back(Task{-1, src + (size_t)c0 * rows * elem, ev, dst + c0 * ld_dst, ld_dst, rows, nc, grid});
+      ++hp->pending;
+    }
+  }
+  hp->cv_task.notify_all();
 }
 
 void hostpipe_wait(HostPipe* hp) {

@@ -532,8 +532,12 @@ def tmax(mx, to_compare, hsq_panel, counter, hsq_list):
 
 def bulkscan_alt_grid(Y, G, K, hsq_list, Covar=None, reml=False, prior_variance=1.0,
                       prior_sample_size=0.0, weights=None, addIntercept=True,
-                      decomp_scheme="eigen", Ut=None, lam=None) -> AltScan:
+                      decomp_scheme="eigen", Ut=None, lam=None, profile: Optional[list] = None) -> AltScan:
     """src/bulkscan.jl:428-526.
+
+    `profile` (not in the reference): a list that receives the p x m matrix `logL1_k` of every grid point in order —
+    the operands of tmax!'s strict comparison; tests use them to show that an h2_panel disagreement is a
+    rounding-level tie of two of them and nothing else.
 
     Divergence from the reference, on purpose: the grid loop at src/bulkscan.jl:510 omits
     `num_of_covar`, which makes the reference throw DimensionMismatch whenever c > 1 (SURVEY
@@ -556,6 +560,8 @@ def bulkscan_alt_grid(Y, G, K, hsq_list, Covar=None, reml=False, prior_variance=
     logLR = weighted_liteqtl(Y0, X0, lam0, hsq_list[0], num_of_covar=c) * LN10
     logL0 = wls_multivar(Y0, X0_base, make_weights(hsq_list[0], lam0), prior, reml=reml).Ell
     logL1 = logLR + np.repeat(logL0, p, axis=0)
+    if profile is not None:
+        profile.append(logL1.copy())
     logL0_all = np.zeros((len(hsq_list), m))
     logL0_all[0, :] = logL0
     h2_panel = np.ones((p, m)) * hsq_list[0]
@@ -565,6 +571,8 @@ def bulkscan_alt_grid(Y, G, K, hsq_list, Covar=None, reml=False, prior_variance=
         logL0_k = wls_multivar(Y0, X0_base, make_weights(h2, lam0), prior, reml=reml).Ell
         logL1_k = logLR_k + np.repeat(logL0_k, p, axis=0)
         logL0_all[k, :] = logL0_k
+        if profile is not None:
+            profile.append(logL1_k)
         tmax(logL1, logL1_k, h2_panel, counter, hsq_list)
     logL0_opt = np.max(logL0_all, axis=0, keepdims=True)
     L = (logL1 - np.repeat(logL0_opt, p, axis=0)) / LN10

@@ -81,12 +81,15 @@ def test_alt_grid(engine, prob, reml):
     from blmm_b200 import bulkscan_alt_grid
     r = bulkscan_alt_grid(prob["Y"], prob["G"], prob["K"], GRID, reml=reml,
                           decomposition=(prob["U"], prob["lam"]), engine=engine)
-    ref = orc.bulkscan_alt_grid(prob["Y"], prob["G"], prob["K"], GRID, reml=reml, Ut=prob["Ut"], lam=prob["lam"])
+    prof = []
+    ref = orc.bulkscan_alt_grid(prob["Y"], prob["G"], prob["K"], GRID, reml=reml, Ut=prob["Ut"], lam=prob["lam"],
+                                profile=prof)
     assert close(r.L, ref.L) < TOL
     assert np.array_equal(np.argmax(r.L, axis=0), np.argmax(ref.L, axis=0))
-    # tmax! counter semantics: identical except where two grid points tie to rounding
-    mism = np.mean(r.h2_panel != ref.h2_panel)
-    assert mism < 1e-4, mism
+    # tmax! counter semantics: identical, except entries where two of the compared logL1 values tie to
+    # rounding — each such entry is proven to be one (no blanket allowance)
+    from parity_helpers import assert_h2_panel_explained
+    assert_h2_panel_explained(r.h2_panel, ref.h2_panel, prof, GRID)
 
 
 def test_alt_grid_covariates(engine, prob):

@@ -83,6 +83,20 @@ def main():
     out["pinned_d2h_gbs_per_gpu"] = rates
     del hbuf
 
+    # what page-locking the caller's arrays for the duration of a call would cost (the alternative to the ring)
+    try:
+        rt = torch.cuda.cudart()
+        a = np.zeros(1 << 28)  # 2 GiB, touched
+        t0 = time.perf_counter()
+        r1 = rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+        t1 = time.perf_counter()
+        r2 = rt.cudaHostUnregister(a.ctypes.data)
+        t2 = time.perf_counter()
+        out["cudaHostRegister_2GiB_ms"] = {"register": (t1 - t0) * 1e3, "unregister": (t2 - t1) * 1e3, "rc": [int(r1), int(r2)]}
+        del a
+    except Exception as ex:  # pragma: no cover
+        out["cudaHostRegister_2GiB_ms"] = {"error": str(ex)[:200]}
+
     def child(name, pinned, want_h2, env):
         e = dict(os.environ)
         e.update(env)
@@ -98,8 +112,16 @@ def main():
     child("pinned_L_only", True, False, {})
     child("pageable_idx", False, True, {"BLMM_B200_H2_TRANSFER": "index"})
     child("pageable_f64", False, True, {"BLMM_B200_H2_TRANSFER": "f64"})
-    for t in (2, 4, 8):
+    for t in (2, 6):
         child(f"threads_{t}_pinned_idx", True, True, {"BLMM_B200_H2_TRANSFER": "index", "BLMM_B200_HOST_THREADS": str(t)})
+        child(f"threads_{t}_pageable_idx", False, True, {"BLMM_B200_H2_TRANSFER": "index", "BLMM_B200_HOST_THREADS": str(t)})
+    # one traced call of the default path (stderr of the child carries the library's phase times)
+    e = dict(os.environ)
+    e.update({"BLMM_B200_TRACE": "1"})
+    for nm, pin in (("pinned", 1), ("pageable", 0)):
+        r = subprocess.run([sys.executable, __file__, "--gpus", str(args.gpus), "--steps", "2", "--m", str(args.m),
+                            "--variant", f"{pin},1"], env=e, capture_output=True, text=True)
+        out["trace_" + nm] = [ln for ln in r.stderr.splitlines() if "blmm trace" in ln][-max(1, args.gpus):]
     print(json.dumps(out), flush=True)
 
 
