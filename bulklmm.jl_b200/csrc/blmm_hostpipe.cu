@@ -23,9 +23,9 @@ namespace blmm {
 
 namespace {
 
-constexpr size_t SLOT_BYTES = 4u << 20;       // Float64 pieces: 4 MB of DMA, 4 MB of host copy per task
-constexpr size_t SLOT_BYTES_INDEX = 1u << 20;  // index pieces expand 8x: 1 MB of DMA, 8 MB of stores per task
-constexpr int NSLOTS = 24;
+constexpr size_t SLOT_BYTES_DEFAULT = 4u << 20;  // Float64 pieces: 4 MB of DMA, 4 MB of host copy per task
+constexpr int NSLOTS_DEFAULT = 24;
+constexpr int NSLOTS_MAX = 256;
 
 struct Task {
   int slot;            // ring slot to release afterwards, or -1: the piece sits in caller-owned pinned staging
@@ -80,8 +80,10 @@ inline void expand_nt(double* dst, const uint8_t* src, int64_t n, const double* 
 
 struct HostPipe {
   int device = 0;
-  uint8_t* ring = nullptr;  // NSLOTS x SLOT_BYTES, pinned
-  cudaEvent_t ev[NSLOTS] = {};
+  uint8_t* ring = nullptr;  // nslots x slot_bytes, pinned
+  size_t slot_bytes = SLOT_BYTES_DEFAULT;
+  int nslots = NSLOTS_DEFAULT;
+  cudaEvent_t ev[NSLOTS_MAX] = {};
   std::mutex mu;
   std::condition_variable cv_task, cv_slot, cv_done;
   std::deque<Task> tasks;
@@ -143,7 +145,11 @@ int default_host_threads() {
 HostPipe* hostpipe_create(int device, int nthreads) {
   HostPipe* hp = new HostPipe();
   hp->device = device;
-  if (cudaMallocHost(&hp->ring, (size_t)NSLOTS * SLOT_BYTES) != cudaSuccess) {
+  // development knobs (tools/e2e_probe.py): ring geometry
+  if (const char* e = getenv("BLMM_B200_RING_SLOT_KB")) hp->slot_bytes = (size_t)std::max(64, atoi(e)) << 10;
+  if (const char* e = getenv("BLMM_B200_RING_SLOTS")) hp->nslots = std::max(4, std::min(NSLOTS_MAX, atoi(e)));
+  const int NSLOTS = hp->nslots;
+  if (cudaMallocHost(&hp->ring, (size_t)NSLOTS * hp->slot_bytes) != cudaSuccess) {
     cudaGetLastError();
     delete hp;
     throw Fail{BLMM_E_CUDA, "cudaMallocHost of the host result ring failed"};
@@ -170,7 +176,7 @@ void hostpipe_destroy(HostPipe* hp) {
   }
   hp->cv_task.notify_all();
   for (auto& t : hp->workers) t.join();
-  for (int i = 0; i < NSLOTS; ++i)
+  for (int i = 0; i < NSLOTS_MAX; ++i)
     if (hp->ev[i]) cudaEventDestroy(hp->ev[i]);
   if (hp->ring) cudaFreeHost(hp->ring);
   delete hp;
@@ -180,7 +186,8 @@ void hostpipe_push(HostPipe* hp, cudaStream_t stream, double* dst, int64_t ld_ds
                    int64_t rows, int64_t cols, const double* grid) {
   if (rows <= 0 || cols <= 0) return;
   const size_t elem = grid ? 1 : 8;
-  const size_t budget = grid ? SLOT_BYTES_INDEX : SLOT_BYTES;
+  // index pieces expand 8x on the host: an eighth of a slot per piece keeps the work per task the same
+  const size_t budget = grid ? std::max<size_t>(hp->slot_bytes / 8, 65536) : hp->slot_bytes;
   const int64_t rows_per_piece = std::min<int64_t>(rows, (int64_t)(budget / elem));
   const int64_t cols_per_piece = (rows_per_piece == rows) ? std::max<int64_t>(1, (int64_t)(budget / (rows * elem))) : 1;
   const uint8_t* src = reinterpret_cast<const uint8_t*>(src_dev);
@@ -196,7 +203,7 @@ void hostpipe_push(HostPipe* hp, cudaStream_t stream, double* dst, int64_t ld_ds
         hp->free_slots.pop_back();
         ++hp->pending;
       }
-      uint8_t* s = hp->ring + (size_t)slot * SLOT_BYTES;
+      uint8_t* s = hp->ring + (size_t)slot * hp->slot_bytes;
       const uint8_t* from = src + ((size_t)c0 * ld_src + r0) * elem;
       const cudaError_t e1 =
           (ld_src == nr || nc == 1)

@@ -1,0 +1,104 @@
+"""Which side is closer to the exact value when the CUDA engine and the float64 oracle disagree?  
+
+    python tools/arbiter_report.py > profiles/arbiter_r02.json          (on a B200 box)
+
+For alt-grid, null-grid and null-exact LODs on a seeded synthetic problem (n = 79, real BXD kinship spectrum shape):
+the entries with the largest |engine - oracle| are re-evaluated in 50-digit arithmetic (oracle/blmm_arbiter.py) from the
+same float64 inputs; for Brent, engine and oracle h2 are compared with the exact maximiser of the same likelihood."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for sub in ("bulklmm.jl_b200", "oracle"):
+    sys.path.insert(0, os.path.join(ROOT, sub))
+import numpy as np
+import blmm_arbiter as arb
+import blmm_oracle as orc
+from blmm_b200 import Engine, bulkscan_alt_grid, bulkscan_null, bulkscan_null_grid, synth
+
+GRID = np.arange(10) / 10.0
+
+
+def worst_entries(a, b, k):
+    d = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    idx = np.argsort(d, axis=None)[-k:]
+    return np.dstack(np.unravel_index(idx, d.shape))[0], float(d.max())
+
+
+def main():
+    eng = Engine(0)
+    n, p, m = 79, 1024, 512
+    Y, G, K = synth.make_problem(n, p, m, seed_g=91, seed_y=92)
+    Ut, lam = orc.decompose(K)
+    dec = (np.asfortranarray(Ut.T), lam)
+    C = np.ones((n, 1))
+    out = {"problem": {"n": n, "p": p, "m": m}, "precision": "mpmath, 50 digits", "cases": {}}
+
+    a = bulkscan_alt_grid(Y, G, K, GRID, decomposition=dec, engine=eng)
+    ref = orc.bulkscan_alt_grid(Y, G, K, GRID, Ut=Ut, lam=lam)
+    w, dmax = worst_entries(a.L, ref.L, 12)
+    rows = []
+    for i, j in w:
+        T = arb.TraitMP(Y[:, j], C, Ut, lam)
+        truth, _, _ = T.alt_grid_entry(G[:, i], list(GRID))
+        side, ee, eo = arb.closer_side(truth, a.L[i, j], ref.L[i, j])
+        rows.append({"marker": int(i), "trait": int(j), "exact": float(truth), "engine_abs_err": ee, "oracle_abs_err": eo,
+                     "closer": "engine" if side < 0 else ("oracle" if side > 0 else "tie")})
+    out["cases"]["alt-grid"] = {"max_rel_engine_vs_oracle": dmax, "h2_panel_mismatch_frac": float(np.mean(a.h2_panel != ref.h2_panel)),
+                                "worst_entries": rows}
+
+    r = bulkscan_null_grid(Y, G, K, GRID, decomposition=dec, engine=eng)
+    ref0 = orc.bulkscan_null_grid(Y, G, K, GRID, Ut=Ut, lam=lam)
+    w, dmax = worst_entries(r.L, ref0.L, 12)
+    rows = []
+    for i, j in w:
+        T = arb.TraitMP(Y[:, j], C, Ut, lam)
+        truth = T.lod(G[:, i], float(ref0.h2_null_list[j]))
+        side, ee, eo = arb.closer_side(truth, r.L[i, j], ref0.L[i, j])
+        rows.append({"marker": int(i), "trait": int(j), "exact": float(truth), "engine_abs_err": ee, "oracle_abs_err": eo,
+                     "closer": "engine" if side < 0 else ("oracle" if side > 0 else "tie")})
+    out["cases"]["null-grid"] = {"max_rel_engine_vs_oracle": dmax, "h2_equal": bool(np.array_equal(r.h2_null_list, ref0.h2_null_list)),
+                                 "worst_entries": rows}
+
+    # Brent: h2 of engine and oracle against the exact optimum of the same REML likelihood
+    ms = 48
+    e = bulkscan_null(Y[:, :ms], G, K, reml=True, prior_variance=0.0, decomposition=dec, engine=eng)
+    Y0, C0 = Ut @ Y[:, :ms], Ut @ C
+    rows = []
+    for j in range(ms):
+        f = orc.fitlmm(Y0[:, j:j + 1], C0, lam, [0.0, 0.0], reml=True)
+        T = arb.TraitMP(Y[:, j], C, Ut, lam)
+        exact = float(T.fit_h2(reml=True, x0=f.h2))
+        rows.append({"trait": j, "exact_h2": exact, "engine_minus_exact": float(e.h2_null_list[j] - exact),
+                     "oracle_minus_exact": float(f.h2 - exact), "engine_minus_oracle": float(e.h2_null_list[j] - f.h2)})
+    d_eo = np.array([abs(x["engine_minus_oracle"]) for x in rows])
+    d_ee = np.array([abs(x["engine_minus_exact"]) for x in rows])
+    d_oe = np.array([abs(x["oracle_minus_exact"]) for x in rows])
+    out["cases"]["brent_h2_reml"] = {
+        "traits": ms, "max_abs_engine_minus_oracle": float(d_eo.max()), "median_abs_engine_minus_oracle": float(np.median(d_eo)),
+        "max_abs_engine_minus_exact": float(d_ee.max()), "max_abs_oracle_minus_exact": float(d_oe.max()),
+        "median_abs_engine_minus_exact": float(np.median(d_ee)), "median_abs_oracle_minus_exact": float(np.median(d_oe)),
+        "note": "Optim Brent stops at |x - mid| <= 2 tol - (hi - lo)/2 with tol = sqrt(eps)|x| + eps (1.5e-8 relative): "
+                "the reference's own h2 is only defined to about that; rows list every trait", "rows": rows}
+    # null-exact LODs at the engine's h2 (the comparison the parity tests make), worst entries vs exact
+    ref2 = orc.bulkscan_null(Y[:, :ms], G, K, reml=True, prior_variance=0.0, Ut=Ut, lam=lam, h2_override=e.h2_null_list)
+    w, dmax = worst_entries(e.L, ref2.L, 8)
+    rows = []
+    for i, j in w:
+        T = arb.TraitMP(Y[:, j], C, Ut, lam)
+        truth = T.lod(G[:, i], float(e.h2_null_list[j]))
+        side, ee, eo = arb.closer_side(truth, e.L[i, j], ref2.L[i, j])
+        rows.append({"marker": int(i), "trait": int(j), "exact": float(truth), "engine_abs_err": ee, "oracle_abs_err": eo,
+                     "closer": "engine" if side < 0 else ("oracle" if side > 0 else "tie")})
+    out["cases"]["null-exact_at_engine_h2"] = {"max_rel_engine_vs_oracle": dmax, "worst_entries": rows}
+    for c in out["cases"].values():
+        if "worst_entries" in c:
+            c["closer_counts"] = {k: sum(1 for x in c["worst_entries"] if x["closer"] == k) for k in ("engine", "oracle", "tie")}
+            c["max_engine_abs_err"] = max(x["engine_abs_err"] for x in c["worst_entries"])
+            c["max_oracle_abs_err"] = max(x["oracle_abs_err"] for x in c["worst_entries"])
+    print(json.dumps(out))
+    eng.close()
+
+
+main()

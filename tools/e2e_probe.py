@@ -112,6 +112,14 @@ def main():
     child("pinned_L_only", True, False, {})
     child("pageable_idx", False, True, {"BLMM_B200_H2_TRANSFER": "index"})
     child("pageable_f64", False, True, {"BLMM_B200_H2_TRANSFER": "f64"})
+    if os.environ.get("PROBE_RING_SWEEP"):
+        for kb, ns in ((256, 96), (512, 64), (1024, 32), (2048, 24), (4096, 24), (8192, 16)):
+            child(f"ring_{kb}KBx{ns}_pageable_idx", False, True,
+                  {"BLMM_B200_H2_TRANSFER": "index", "BLMM_B200_RING_SLOT_KB": str(kb), "BLMM_B200_RING_SLOTS": str(ns)})
+        for t in (4, 8, 10):
+            child(f"threads_{t}_pinned_idx", True, True, {"BLMM_B200_H2_TRANSFER": "index", "BLMM_B200_HOST_THREADS": str(t)})
+        for t in (10, 20):
+            child(f"threads_{t}_pageable_idx", False, True, {"BLMM_B200_H2_TRANSFER": "index", "BLMM_B200_HOST_THREADS": str(t)})
     for t in (2, 6):
         child(f"threads_{t}_pinned_idx", True, True, {"BLMM_B200_H2_TRANSFER": "index", "BLMM_B200_HOST_THREADS": str(t)})
         child(f"threads_{t}_pageable_idx", False, True, {"BLMM_B200_H2_TRANSFER": "index", "BLMM_B200_HOST_THREADS": str(t)})
