@@ -99,6 +99,7 @@ struct Rotated {
 
 struct Rotated;
 void rotate_markers(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space, cudaStream_t stream);
+void rotate_markers_aside(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space, cudaStream_t after);
 void rotate_traits(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space);
 
 Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool with_markers,
@@ -135,7 +136,7 @@ Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool
   R.Y0 = nullptr;
   if (with_traits) rotate_traits(ctx, pr, R, mem_space);
   R.G0 = nullptr;
-  if (with_markers) rotate_markers(ctx, pr, R, mem_space, ctx->stream);
+  if (with_markers) rotate_markers_aside(ctx, pr, R, mem_space, ctx->stream);
   return R;
 }
 
@@ -153,6 +154,19 @@ void rotate_markers(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_s
   ctx->launches += launch_rotate(R.dU, dG, pr->n, R.G0, R.n_pad, R.n_pad, R.n, pr->p, stream);
 }
 
+// Staging and rotating the markers depends on nothing but G and U: it runs on the third stream, beside whatever the
+// other two are doing (trait rotation / statistics / Brent fit; covariates and weight constants); `consumer` is made
+// to wait for it by wait_markers() right before the first kernel that reads G0.
+void rotate_markers_aside(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space, cudaStream_t after) {
+  ws<double>(ctx, S_G_IN, mem_space == BLMM_MEM_HOST ? (size_t)pr->n * pr->p : 1);  // (re)allocations first: cudaFree
+  ws<double>(ctx, S_G0, (size_t)R.n_pad * pr->p);                                    // synchronises the device
+  CUDA_TRY(cudaEventRecord(ctx->aux_fork_ev, after));  // dU (and a previous call's readers of G0) are ordered before
+  CUDA_TRY(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork_ev, 0));
+  rotate_markers(ctx, pr, R, mem_space, ctx->aux_stream);
+  CUDA_TRY(cudaEventRecord(ctx->aux_done_ev, ctx->aux_stream));
+}
+void wait_markers(blmm_ctx* ctx, cudaStream_t consumer) { CUDA_TRY(cudaStreamWaitEvent(consumer, ctx->aux_done_ev, 0)); }
+
 // The marker side of a grid scan (G -> U'G -> weight-folded marker operand) depends only on G, U and the
 // per-h2 weight constants, the trait side only on Y: the two chains are latency-bound on their own, so the
 // marker chain runs on the second stream while the main stream does the traits.  Returns after queueing;
@@ -164,7 +178,7 @@ void fork_marker_side(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem
     CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
   }
   R.p = pr->p;
-  rotate_markers(ctx, pr, R, mem_space, ctx->copy_stream);
+  wait_markers(ctx, ctx->copy_stream);  // queued by the caller before the covariate chain (rotate_markers_aside)
   ctx->launches += launch_marker_operand(R.G0, R.p, p_pad, R.n, R.n_pad, R.c, nk, wc, fold_sw, Mop, ctx->d_flags,
                                          ctx->copy_stream);
   CUDA_TRY(cudaEventRecord(ctx->join_ev, ctx->copy_stream));
@@ -218,11 +232,6 @@ unsigned long long* fresh_unit_counter(blmm_ctx* ctx) {
 }
 
 void run_scan(blmm_ctx* ctx, ScanParams P) {
-  if (!ctx->buf[S_LOGTAB]) {
-    double* tab = ws<double>(ctx, S_LOGTAB, scan_logtab_doubles());
-    ctx->launches += launch_logtab(tab, ctx->stream);
-  }
-  P.logtab = reinterpret_cast<const double*>(ctx->buf[S_LOGTAB]);
   if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   if (P.nq <= scan_max_nq(P.nk)) {
     const int launched = launch_scan(P, ctx->sm_count, ctx->stream);
@@ -233,7 +242,7 @@ void run_scan(blmm_ctx* ctx, ScanParams P) {
     static_assert(SCAN_TT == 128 && SCAN_MT == 64, "packing shared with the streamed GRID kernel");
     StreamParams Q{};
     Q.Mop = P.Mop; Q.Xop = P.Top; Q.e = P.e; Q.et = P.et; Q.tile_k0 = P.tile_k0; Q.n_tiles_dev = P.n_tiles_dev;
-    Q.col_map = P.col_map; Q.grid = P.grid; Q.logtab = P.logtab; Q.ngrid = P.ngrid; Q.L = P.L; Q.L0 = P.L0;
+    Q.col_map = P.col_map; Q.grid = P.grid; Q.ngrid = P.ngrid; Q.L = P.L; Q.L0 = P.L0;
     Q.H2 = P.H2; Q.colmax = P.colmax; Q.ldL = P.ldL; Q.nq = P.nq; Q.p = P.p; Q.p_pad = P.p_pad; Q.m = P.m;
     Q.xcol_pad = P.tcol_pad; Q.tcol_pad = P.tcol_pad; Q.n_tt = P.n_tiles_t; Q.nk = P.nk;
     Q.argmax_mode = P.argmax_mode; Q.half_n = P.half_n;
@@ -273,6 +282,7 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   // second stream: covariate rotation -> weight constants -> marker rotation -> marker operand;
   // main stream: trait rotation, then (after the weight constants) the trait statistics
   Rotated R = rotate_inputs(ctx, pr, ms, false, false, true);
+  rotate_markers_aside(ctx, pr, R, ms, ctx->stream);  // third stream: G -> U'G beside the covariate chain
   ctx->launches += launch_weight_consts(d_grid, nk, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags,
                                         ctx->copy_stream);
   CUDA_TRY(cudaEventRecord(ctx->wc_ev, ctx->copy_stream));
@@ -533,6 +543,7 @@ int bulkscan_exact(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, do
   const int64_t p_pad = round_up(p, mt);
   WeightConsts wc0 = weight_ws(ctx, 0, R.n_pad, R.c);
   double* Mop = ws<double>(ctx, S_MOP, (size_t)R.n_pad * p_pad);
+  wait_markers(ctx, ctx->stream);  // U'G was computed on the third stream meanwhile
   ctx->launches += launch_marker_operand(R.G0, p, p_pad, R.n, R.n_pad, R.c, 1, wc0, false, Mop, ctx->d_flags, ctx->stream);
   const int cg = R.c + 2;
   const int64_t n_tt = (m + 63) / 64;
@@ -542,15 +553,10 @@ int bulkscan_exact(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, do
   double* dyinv = ws<double>(ctx, S_DYINV, slots);
   ctx->launches += launch_exact_columns(Yr, h2, R.lambda, R.C0, m, slots, R.n, R.n_pad, R.c, Xop, xcol_pad, dyinv,
                                         ctx->d_flags, ctx->stream);
-  if (!ctx->buf[S_LOGTAB]) {
-    double* tab = ws<double>(ctx, S_LOGTAB, scan_logtab_doubles());
-    ctx->launches += launch_logtab(tab, ctx->stream);
-  }
   StreamParams P{};
   P.Mop = Mop;
   P.Xop = Xop;
   P.dyinv = dyinv;
-  P.logtab = reinterpret_cast<const double*>(ctx->buf[S_LOGTAB]);
   double* dL = dev ? L_out : ws<double>(ctx, S_L, (size_t)p * m);
   P.L = dL;
   P.ldL = dev ? ld : p;
@@ -605,6 +611,7 @@ int scan_alt(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, double* 
                                  nullptr, ctx->d_flags, ctx->stream);
   double* dlod = dev ? lod_out : ws<double>(ctx, S_L, p);
   double* dh2 = h2_each_out ? (dev ? h2_each_out : ws<double>(ctx, S_H2P, p)) : nullptr;
+  wait_markers(ctx, ctx->stream);  // U'G was computed on the third stream meanwhile
   const int launched = launch_scan_alt(Yr, R.G0, p, R.n, R.n_pad, R.c, R.C0, R.lambda, lik_of(o), o->optim_interval,
                                        misc, misc + 2, dlod, dh2, ctx->stream);
   if (!launched) throw Fail{BLMM_E_INVALID, "unsupported covariate count"};
@@ -649,6 +656,7 @@ int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const 
   ctx->launches += launch_null_residual(Yr, R.n, R.n_pad, R.c, wc, z, zrss, ctx->stream);
   const int64_t p_pad = round_up(p, SCAN_MT);
   double* Mop = ws<double>(ctx, S_MOP, (size_t)R.n_pad * p_pad);
+  wait_markers(ctx, ctx->stream);  // U'G was computed on the third stream meanwhile
   ctx->launches += launch_marker_operand(R.G0, p, p_pad, R.n, R.n_pad, R.c, 1, wc, false, Mop, ctx->d_flags, ctx->stream);
 
   const int64_t ncol = nperms + 1;
@@ -889,6 +897,7 @@ int guarded(blmm_ctx* ctx, F&& f) {
     // leave nothing in flight that still writes into the caller's arrays, and no stale device flag
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     try {
       hostpipe_wait(ctx->pipe);
     } catch (...) {
@@ -932,6 +941,9 @@ int blmm_create(blmm_ctx** out, int device) {
   bool ok = cudaSetDevice(device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->aux_fork_ev, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->aux_done_ev, cudaEventDisableTiming) == cudaSuccess &&
             cudaMalloc(&ctx->d_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaMemset(ctx->d_flags, 0, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
             cudaMallocHost(&ctx->h_flags, FLAG_COUNT * sizeof(int)) == cudaSuccess &&
@@ -981,6 +993,7 @@ void blmm_destroy(blmm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   hostpipe_destroy(ctx->pipe);
   for (int s = 0; s < S_COUNT; ++s)
     if (ctx->buf[s]) cudaFree(ctx->buf[s]);
@@ -997,6 +1010,9 @@ void blmm_destroy(blmm_ctx* ctx) {
     if (ctx->idx_ev[i]) cudaEventDestroy(ctx->idx_ev[i]);
   }
   if (ctx->h_idx) cudaFreeHost(ctx->h_idx);
+  if (ctx->aux_fork_ev) cudaEventDestroy(ctx->aux_fork_ev);
+  if (ctx->aux_done_ev) cudaEventDestroy(ctx->aux_done_ev);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -125,45 +125,73 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
   atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
-constexpr int LOGTAB_N = 128;  // entries of the log10 table (launch_logtab)
+// ---------------------------------------------------------------------------------------------
+// The scan kernels' LOD: a 512-entry table built in shared memory by the kernel itself, scaled by n/2.
+// ---------------------------------------------------------------------------------------------
+constexpr int LTAB = 512;  // entries of the in-kernel logarithm table
 
-// ---------------------------------------------------------------------------------------------
-// log10 for the final epilogue.  The FP64 pipe is shared by DMMA and scalar double arithmetic on
-// B200 (profiles/fp64_peak_r01.json: mixed loop), so the logarithm is kept to ~12 FP64
-// operations: v = 2^e * m, m in [0.75, 1.5); a 128-entry table gives rcp ~ 1/c and -log10(rcp)
-// for the interval of m; r = m*rcp - 1 (|r| <= 2^-7); log1p(r) by an 8-term series.  The two
-// intervals touching 1 use rcp = 1 exactly, so results keep full relative accuracy as v -> 1
-// (LOD -> 0).  Absolute error ~1e-16, far inside the 1e-8 parity tolerance.
+// tab[i] = {rcp, (n/2) log10(rcp)} for the i-th interval of m in [0.75, 1.5): 256 intervals over [0.75, 1), 256 over
+// [1, 1.5); the two intervals touching 1 use rcp = 1 exactly.  Called by all threads of the block (nthreads >= 1).
+__device__ __forceinline__ void build_lod_table(double2* tab, int tid, int nthreads, double half_n) {
+  for (int i = tid; i < LTAB; i += nthreads) {
+    double c;
+    if (i == LTAB / 2 - 1 || i == LTAB / 2)
+      c = 1.0;
+    else if (i < LTAB / 2)
+      c = 0.75 + ((double)i + 0.5) * (0.25 / (LTAB / 2));
+    else
+      c = 1.0 + ((double)(i - LTAB / 2) + 0.5) * (0.5 / (LTAB / 2));
+    const double rcp = 1.0 / c;
+    tab[i] = make_double2(rcp, (rcp == 1.0) ? 0.0 : half_n * log10(rcp));
+  }
+}
+
+// LOD = -(n/2) log10(v) for the final epilogue, ~8 FP64 operations (the FP64 pipe is shared with DMMA).
+// v = 2^e * m, m in [0.75, 1.5); the table gives rcp ~ 1/c and (n/2) log10(rcp) for m's interval
+// (256 intervals over [0.75, 1), 256 over [1, 1.5)); r = m*rcp - 1, |r| < 2^-9; log1p(r) by a 5-term
+// series.  The two intervals touching 1 use rcp = 1 exactly, so LODs keep full relative accuracy as
+// v -> 1 (LOD -> 0): relative error <= r^5/6 ~ 1e-16 there, absolute error ~1e-19 * n elsewhere.
 // `special` is raised for operands outside the positive normal range (fixed up by the caller).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double fast_log10(double v, const double2* __restrict__ tab, bool& special) {
+__device__ __forceinline__ double fast_lod(double v, const double2* __restrict__ tab, double c_ln, double c_e,
+                                           bool& special) {
   const int hi = __double2hiint(v), lo = __double2loint(v);
   const int ix = hi - 0x3fe80000;
   const int e = ix >> 20;
   const double m = __hiloint2double(hi - (e << 20), lo);
-  const double2 t = tab[(ix >> 13) & (LOGTAB_N - 1)];
+  const double2 t = tab[(ix >> 11) & (LTAB - 1)];
   const double r = fma(m, t.x, -1.0);
-  double q = fma(r, -1.0 / 8.0, 1.0 / 7.0);
-  q = fma(q, r, -1.0 / 6.0);
-  q = fma(q, r, 1.0 / 5.0);
-  q = fma(q, r, -1.0 / 4.0);
-  q = fma(q, r, 1.0 / 3.0);
-  q = fma(q, r, -1.0 / 2.0);
-  q = fma(q, r, 1.0);
-  const double lp = q * r;
+  // -(n/2) log10(e) * log1p(r) = r * (k1 + r (k2 + r (k3 + r (k4 + r k5)))), k_i = c_ln * (-1)^(i+1) / i: the
+  // scale is folded into the coefficients and the last multiply into the final FMA (8 FP64 operations in all)
+  double q = fma(r, c_ln * (1.0 / 5.0), c_ln * (-1.0 / 4.0));
+  q = fma(q, r, c_ln * (1.0 / 3.0));
+  q = fma(q, r, c_ln * (-1.0 / 2.0));
+  q = fma(q, r, c_ln);
   special |= (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
-  return fma(lp, 0.43429448190325182765, fma((double)e, 0.30102999566398119521, t.y));
+  // c_ln = -(n/2) log10(e), c_e = -(n/2) log10(2), t.y = -(n/2) * (-log10 rcp)
+  return fma(q, r, fma((double)e, c_e, t.y));
 }
 
-// IEEE results for the operands fast_log10 flags: v = 0 (r^2 = 1) -> -inf as log10 (a subnormal
-// v, unreachable as 1 - r^2, is treated as 0); v < 0 -> NaN (Julia's log10 throws there);
-// inf / NaN pass through.
-__device__ __forceinline__ double fix_log10(double v, double res) {
+// IEEE results for the operands fast_lod flags: v = 0 (r^2 = 1) -> LOD = +inf (a subnormal v,
+// unreachable as 1 - r^2, is treated as 0); v < 0 -> NaN (Julia's log10 throws there); v = +inf ->
+// -inf; NaN passes through.
+__device__ __forceinline__ double fix_lod(double v, double res) {
   const int hi = __double2hiint(v);
-  res = ((unsigned)hi < 0x00100000u) ? -INFINITY : res;
+  res = ((unsigned)hi < 0x00100000u) ? INFINITY : res;
   res = (hi < 0) ? __longlong_as_double(0x7ff8000000000000LL) : res;
-  res = (hi >= 0x7ff00000) ? v : res;
+  res = (hi >= 0x7ff00000) ? -v : res;
   return res;
+}
+
+
+// 1 / a to full double precision without the division sequence: the hardware's ~20-bit reciprocal estimate and two
+// Newton steps (4 FP64 operations; the result may differ from the correctly rounded quotient in the last bit).
+__device__ __forceinline__ double fast_rcp(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  return fma(r, e, r);
 }
 
 }  // namespace blmm

@@ -47,6 +47,8 @@ struct blmm_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap the scan (host-buffer calls)
+  cudaStream_t aux_stream = nullptr;   // staging + rotation of the markers, beside the other two
+  cudaEvent_t aux_fork_ev = nullptr, aux_done_ev = nullptr;
   cudaEvent_t chunk_ev[blmm::MAX_CHUNK] = {};
   cudaEvent_t idx_ev[blmm::MAX_CHUNK] = {};  // chunk's h2 index panel has landed in h_idx
   uint8_t* h_idx = nullptr;                   // pinned staging of the h2 index panel (host-buffer alt-grid calls)

@@ -137,7 +137,6 @@ struct ScanParams {
   const int* n_tiles_dev;  // device scalar: number of trait tiles in use; nullptr => n_tiles_t
   const int* col_map;      // [tcol_pad] packed column -> output column (-1 = padding); nullptr => identity
   const double* grid;      // device copy of the h2 grid (for the h2 panel), ngrid <= 255 values
-  const double* logtab;    // log10 table of the final epilogue (launch_logtab)
   int ngrid;
   double* L;               // p x m output, ld = ldL (nullptr => not stored)
   double* L0;              // if non-null: output column 0 goes here (length p) and column s >= 1 goes to
@@ -162,9 +161,6 @@ constexpr int SCAN_TT = 128;  // traits per CTA tile
 constexpr int SCAN_MT = 64;   // markers per CTA tile
 // Largest number of K-chunks the shared-memory-resident kernel supports for a k-list of nk.
 int scan_max_nq(int nk);
-// the 128-entry {1/c, -log10(1/c)} table used by the kernel's logarithm; built once per context
-int scan_logtab_doubles();
-int launch_logtab(double* tab, cudaStream_t stream);
 int launch_scan(const ScanParams& P, int sm_count, cudaStream_t stream);
 
 // ---- the K-streamed scans (blmm_scan_stream.cu) -------------------------------------------------
@@ -179,7 +175,6 @@ struct StreamParams {
   const int* n_tiles_dev;  // device scalar: trait tiles in use, or nullptr => n_tt
   const int* col_map;      // packed column -> output column (-1 = padding); nullptr => identity
   const double* grid;      // h2 grid (device), GRID mode h2 panel
-  const double* logtab;
   int ngrid;
   double* L;
   double* L0;

@@ -36,7 +36,6 @@ constexpr int NWARPS = 2 * WT_WARPS;
 constexpr int NTHREADS = 32 * NWARPS;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int GRID_MAX = 256;
-constexpr int LTAB = 512;  // entries of the in-kernel logarithm table
 
 static_assert(NWARPS == 16 && NTHREADS == 512, "ping-pong barrier counts assume 16 warps");
 
@@ -84,42 +83,6 @@ __device__ __forceinline__ void dmma884_zero(double& c0, double& c1, double a, d
       : "d"(a), "d"(b), "d"(0.0));
 }
 
-// LOD = -(n/2) log10(v) for the final epilogue, ~8 FP64 operations (the FP64 pipe is shared with DMMA).
-// v = 2^e * m, m in [0.75, 1.5); the table gives rcp ~ 1/c and (n/2) log10(rcp) for m's interval
-// (256 intervals over [0.75, 1), 256 over [1, 1.5)); r = m*rcp - 1, |r| < 2^-9; log1p(r) by a 5-term
-// series.  The two intervals touching 1 use rcp = 1 exactly, so LODs keep full relative accuracy as
-// v -> 1 (LOD -> 0): relative error <= r^5/6 ~ 1e-16 there, absolute error ~1e-19 * n elsewhere.
-// `special` is raised for operands outside the positive normal range (fixed up by the caller).
-__device__ __forceinline__ double fast_lod(double v, const double2* __restrict__ tab, double c_ln, double c_e,
-                                           bool& special) {
-  const int hi = __double2hiint(v), lo = __double2loint(v);
-  const int ix = hi - 0x3fe80000;
-  const int e = ix >> 20;
-  const double m = __hiloint2double(hi - (e << 20), lo);
-  const double2 t = tab[(ix >> 11) & (LTAB - 1)];
-  const double r = fma(m, t.x, -1.0);
-  // -(n/2) log10(e) * log1p(r) = r * (k1 + r (k2 + r (k3 + r (k4 + r k5)))), k_i = c_ln * (-1)^(i+1) / i: the
-  // scale is folded into the coefficients and the last multiply into the final FMA (8 FP64 operations in all)
-  double q = fma(r, c_ln * (1.0 / 5.0), c_ln * (-1.0 / 4.0));
-  q = fma(q, r, c_ln * (1.0 / 3.0));
-  q = fma(q, r, c_ln * (-1.0 / 2.0));
-  q = fma(q, r, c_ln);
-  special |= (unsigned)(hi - 0x00100000) >= 0x7fe00000u;
-  // c_ln = -(n/2) log10(e), c_e = -(n/2) log10(2), t.y = -(n/2) * (-log10 rcp)
-  return fma(q, r, fma((double)e, c_e, t.y));
-}
-
-// IEEE results for the operands fast_lod flags: v = 0 (r^2 = 1) -> LOD = +inf (a subnormal v,
-// unreachable as 1 - r^2, is treated as 0); v < 0 -> NaN (Julia's log10 throws there); v = +inf ->
-// -inf; NaN passes through.
-__device__ __forceinline__ double fix_lod(double v, double res) {
-  const int hi = __double2hiint(v);
-  res = ((unsigned)hi < 0x00100000u) ? INFINITY : res;
-  res = (hi < 0) ? __longlong_as_double(0x7ff8000000000000LL) : res;
-  res = (hi >= 0x7ff00000) ? -v : res;
-  return res;
-}
-
 // HAS_E = false: one-element k-lists with e = 1 (null-grid bins, permutations) — no running minimum,
 // no counter, no h2 panel.  COLMAX: also reduce the per-column maximum (permutation thresholds).
 template <int NQ, bool ARGMAX, bool HAS_E, bool COLMAX>
@@ -153,19 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
     for (int i = 0; i < 8; ++i) mbar_init(&turn[i], 2);  // the two warps of the other group on the sub-partition
     mbar_fence_init();
   }
-  {
-    // logarithm table, scaled by -(n/2) so that the epilogue produces the LOD directly
-    const int i = tid;
-    double c;
-    if (i == LTAB / 2 - 1 || i == LTAB / 2)
-      c = 1.0;
-    else if (i < LTAB / 2)
-      c = 0.75 + ((double)i + 0.5) * (0.25 / (LTAB / 2));
-    else
-      c = 1.0 + ((double)(i - LTAB / 2) + 0.5) * (0.5 / (LTAB / 2));
-    const double rcp = 1.0 / c;
-    logtab[i] = make_double2(rcp, (rcp == 1.0) ? 0.0 : P.half_n * log10(rcp));
-  }
+  build_lod_table(logtab, tid, NTHREADS, P.half_n);
   if (P.grid && tid < P.ngrid) grid_s[tid] = P.grid[tid];
   __syncthreads();
 
@@ -529,21 +480,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
 #endif
 }
 
-__global__ void logtab_kernel(double* tab) {
-  const int i = threadIdx.x;
-  if (i >= LOGTAB_N) return;
-  double c;
-  if (i == 63 || i == 64)
-    c = 1.0;
-  else if (i < 64)
-    c = 0.75 + ((double)i + 0.5) / 256.0;
-  else
-    c = 1.0 + ((double)(i - 64) + 0.5) / 128.0;
-  const double rcp = 1.0 / c;
-  tab[2 * i] = rcp;
-  tab[2 * i + 1] = (rcp == 1.0) ? 0.0 : -log10(rcp);
-}
-
 template <int NQ, bool ARGMAX, bool HAS_E, bool COLMAX>
 void launch_one(const ScanParams& P, int sm_count, cudaStream_t stream) {
   const SmemPlan plan = plan_smem(NQ);
@@ -572,13 +508,6 @@ void launch_nq(const ScanParams& P, int sm_count, cudaStream_t stream) {
 int scan_max_nq(int nk) {
   (void)nk;
   return 5;
-}
-
-int scan_logtab_doubles() { return 2 * LOGTAB_N; }
-
-int launch_logtab(double* tab, cudaStream_t stream) {
-  logtab_kernel<<<1, LOGTAB_N, 0, stream>>>(tab);
-  return 1;
 }
 
 #ifdef BLMM_SCAN_TIMING

@@ -34,7 +34,7 @@ constexpr int GRID_MAX = 256;
 constexpr int ST_TG = 8;                  // warps along the trait dimension
 constexpr int ST_WARPS = 2 * ST_TG;       // x 2 along the marker dimension
 constexpr int BAND_DEFAULT = 8;           // trait tiles per rasterisation band (StreamParams::band overrides)
-constexpr size_t ST_FIXED_SMEM = (size_t)LOGTAB_N * 16 + GRID_MAX * 8 + 128;
+constexpr size_t ST_FIXED_SMEM = (size_t)LTAB * 16 + GRID_MAX * 8 + 128;
 
 enum { MODE_EXACT = 0, MODE_GRID = 1 };
 
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
   const int NS = plan.nstage < ipu_cap ? plan.nstage : ipu_cap;
   double* stages = reinterpret_cast<double*>(smem_raw);
   double2* logtab = reinterpret_cast<double2*>(stages + NS * plan.stage_doubles);
-  double* grid_s = reinterpret_cast<double*>(logtab + LOGTAB_N);
+  double* grid_s = reinterpret_cast<double*>(logtab + LTAB);
   uint64_t* full = reinterpret_cast<uint64_t*>(grid_s + GRID_MAX);  // [4]
   int* rel_cnt = reinterpret_cast<int*>(full + 4);                  // [4]
 
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
     for (int o = 0; o < 3; ++o)
       uq[o] = P.unit_counter ? (long long)atomicAdd(P.unit_counter, 1ULL) : (long long)blockIdx.x + (long long)o * gridDim.x;
   }
-  if (tid < LOGTAB_N) logtab[tid] = reinterpret_cast<const double2*>(P.logtab)[tid];
+  build_lod_table(logtab, tid, 32 * ST_WARPS, P.half_n);  // scaled by n/2: the epilogue yields the LOD directly
   if (MODE == MODE_GRID && P.grid && tid < P.ngrid) grid_s[tid] = P.grid[tid];
   __syncthreads();
 
@@ -268,9 +268,10 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
             double dg = acc[a][NB - 1][cc];
 #pragma unroll
             for (int b = 1; b < NB - 1; ++b) dg = fma(-acc[a][b][cc], acc[a][b][cc], dg);
+            // v = 1 - r^2 = 1 - num^2 dyinv / dg through a Newton reciprocal (4 FP64 operations) instead of the
+            // division sequence: the FP64 pipe is shared with the DMMAs of the other warps
             const double num = acc[a][0][cc];
-            const double r2 = (num * num) * dyi[cc] / dg;
-            vmin[a][0][cc] = 1.0 - r2;
+            vmin[a][0][cc] = fma(-((num * num) * dyi[cc]), fast_rcp(dg), 1.0);
           }
       }
     }
@@ -278,19 +279,21 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
     // final epilogue: one logarithm per output, streaming stores
     constexpr int NBO = (MODE == MODE_EXACT) ? 1 : NB;
     bool special = false;
+    const double c_ln = -P.half_n * 0.43429448190325182765;
+    const double c_e = -P.half_n * 0.30102999566398119521;
 #pragma unroll
     for (int a = 0; a < MA; ++a)
 #pragma unroll
       for (int b = 0; b < NBO; ++b)
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) lod[a][b][cc] = fast_log10(vmin[a][b][cc], logtab, special);
+        for (int cc = 0; cc < 2; ++cc) lod[a][b][cc] = fast_lod(vmin[a][b][cc], logtab, c_ln, c_e, special);
     if (__any_sync(0xffffffffu, special)) {
 #pragma unroll
       for (int a = 0; a < MA; ++a)
 #pragma unroll
         for (int b = 0; b < NBO; ++b)
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) lod[a][b][cc] = fix_log10(vmin[a][b][cc], lod[a][b][cc]);
+          for (int cc = 0; cc < 2; ++cc) lod[a][b][cc] = fix_lod(vmin[a][b][cc], lod[a][b][cc]);
     }
     const int k0 = (MODE == MODE_GRID && P.tile_k0) ? P.tile_k0[tt] : 0;
     const int kbase = ARGMAX ? k0 : 0;
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 1) scan_stream_kernel(const Str
 #pragma unroll
         for (int a = 0; a < MA; ++a) {
           const int i = i_base + a * 8;
-          const double l = -P.half_n * lod[a][b][cc];
+          const double l = lod[a][b][cc];
           if (i < P.p) {
             if (Lc) st_stream(Lc + i, l);
             if (MODE == MODE_GRID && Hc) {

@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from parity_helpers import assert_h2_panel_explained
+from parity_helpers import assert_h2_panel_explained, H2_TOL
 
 import blmm_oracle as orc
 from blmm_b200 import BlmmError, bulkscan, bulkscan_alt_grid, bulkscan_null_grid, scan, synth
@@ -120,7 +120,7 @@ def test_scan_perms_given_decomposition_exact(engine):
     assert rel(r.lod, Lref[:, 0]) < 1e-8
     assert rel(r.L_perms, Lref[:, 1:]) < 1e-8
     assert np.array_equal(np.argmax(r.L_perms, axis=0), np.argmax(Lref[:, 1:], axis=0))
-    assert abs(r.h2_null - ref["h2_null"]) < 2e-6
+    assert abs(r.h2_null - ref["h2_null"]) < H2_TOL
 
 
 def test_error_paths(engine):

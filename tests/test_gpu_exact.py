@@ -7,7 +7,7 @@ so null-exact is checked in two stages: h2 within 2e-6 absolute of the oracle's 
 import numpy as np
 import pytest
 
-from parity_helpers import assert_h2_panel_explained
+from parity_helpers import assert_h2_panel_explained, H2_TOL
 
 import blmm_oracle as orc
 from blmm_b200 import bulkscan, bulkscan_alt_grid, bulkscan_null, bulkscan_null_grid, scan, synth
@@ -35,7 +35,7 @@ def check_exact(engine, Y, G, K, Ut, lam, dec, Covar=None, reml=False, prior=(1.
     sub = slice(0, min(brent_cols, Y.shape[1]))
     ref = orc.bulkscan_null(Y[:, sub], G[:, :3], K, Covar=Covar, reml=reml, prior_variance=prior[0],
                             prior_sample_size=prior[1], Ut=Ut, lam=lam)
-    assert np.max(np.abs(r.h2_null_list[sub] - ref.h2_null_list)) < 2e-6
+    assert np.max(np.abs(r.h2_null_list[sub] - ref.h2_null_list)) < H2_TOL
     # stage 2: LODs at the engine's own h2
     ref2 = orc.bulkscan_null(Y, G, K, Covar=Covar, reml=reml, prior_variance=prior[0], prior_sample_size=prior[1],
                              Ut=Ut, lam=lam, h2_override=r.h2_null_list)
@@ -77,7 +77,7 @@ def test_scan_null_single_trait(engine):
         y = Y[:, 2:3]
         r = scan(y, G, K, reml=reml, decomposition=dec, engine=engine)
         ref = orc.scan(y, G, K, reml=reml, Ut=Ut, lam=lam)
-        assert abs(r.h2_null - ref["h2_null"]) < 2e-6
+        assert abs(r.h2_null - ref["h2_null"]) < H2_TOL
         assert abs(r.sigma2_e - ref["sigma2_e"]) < 1e-5 * ref["sigma2_e"]
         assert rel(r.lod, ref["lod"]) < 1e-5  # h2 differs at the 1e-7 level through Brent
         # and identical to bulkscan null-exact with scan's prior (0, 0)
@@ -104,7 +104,7 @@ def test_large_n_grid_methods_streamed(engine):
     perm = synth.make_perm_indices(250, 200, rndseed=3)
     s = scan(Y[:, 1:2], G, K, permutation_test=True, perm_idx=perm, decomposition=dec, engine=engine)
     sref = orc.scan(Y[:, 1:2], G, K, permutation_test=True, perm_idx=perm, Ut=Ut, lam=lam)
-    assert abs(s.h2_null - sref["h2_null"]) < 2e-6
+    assert abs(s.h2_null - sref["h2_null"]) < H2_TOL
     assert rel(s.L_perms, sref["L_perms"]) < 1e-5
     assert np.array_equal(s.max_lod, s.L_perms.max(axis=0))
 
@@ -136,7 +136,7 @@ def test_scan_perms_nonzero_h2(engine):
             continue
         hits += 1
         ref = orc.scan(y, G, K, permutation_test=True, perm_idx=perm, reml=True, Ut=Ut, lam=lam)
-        assert abs(s.h2_null - ref["h2_null"]) < 2e-6
+        assert abs(s.h2_null - ref["h2_null"]) < H2_TOL
         assert rel(s.lod, ref["lod"]) < 1e-5
         assert rel(s.L_perms, ref["L_perms"]) < 1e-5
         # un-permuted column == scan_null of the same trait

@@ -11,7 +11,7 @@ optimum (the arbiter measures this), so two FP64 implementations agree to a few 
 import numpy as np
 import pytest
 
-from parity_helpers import rel
+from parity_helpers import H2_TOL, rel
 
 import blmm_oracle as orc
 from blmm_b200 import bulkscan_alt_grid, bulkscan_null, bulkscan_null_grid, scan, synth, thresholds_from_max
@@ -19,7 +19,6 @@ from blmm_b200 import bulkscan_alt_grid, bulkscan_null, bulkscan_null_grid, scan
 pytestmark = pytest.mark.gpu
 GRID = np.arange(10) / 10.0
 TOL = 1e-8
-H2_TOL = 2e-6  # absolute; the observed maximum is printed by tools/arbiter_report.py (profiles/arbiter_r02.json)
 
 
 def oracle_perm_lods_at_h2(y, G, K, Ut, lam, perm, h2, n):
