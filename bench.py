@@ -253,13 +253,22 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    cpu_group = None
     if world > 1:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-        # a CPU-side barrier for the phases in which rank 0 drives every GPU through ONE multi-GPU context: the other
-        # ranks must not sit in an NCCL barrier (a spinning kernel on their GPU would time-slice with rank 0's work)
-        cpu_group = dist.new_group(backend="gloo")
+
+    def wait_for_rank0(tag):
+        """CPU-side wait (the rendezvous store, no GPU work) for the phases in which rank 0 drives every GPU through
+        ONE multi-GPU context: the other ranks must not sit in an NCCL barrier meanwhile — a spinning kernel on their
+        GPU would time-slice with rank 0's work there."""
+        if world == 1:
+            return
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set(tag, "1")
+        else:
+            store.wait([tag], datetime.timedelta(seconds=3600))
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     METHODS = {"alt-grid": L.METHOD_ALT_GRID, "null-grid": L.METHOD_NULL_GRID, "null-exact": L.METHOD_NULL_EXACT,
@@ -455,8 +464,7 @@ def main():
                     out["note"] += "  [only this rank's GPU was visible: single-GPU call]"
             except (RuntimeError, MemoryError) as ex:  # pinned allocation of a very large result can fail on small hosts
                 out = {"value": None, "unit": "tests/s", "error": str(ex)[:200]}
-        if world > 1:
-            dist.barrier(group=cpu_group)
+        wait_for_rank0("blmm_e2e_done")
         return out
 
     job = Job(args.workload)
@@ -547,7 +555,7 @@ def main():
                 "reference_published": README_REF}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier(group=cpu_group)
+        wait_for_rank0("blmm_line_printed")
         dist.destroy_process_group()
 
 

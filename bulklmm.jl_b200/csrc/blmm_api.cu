@@ -232,6 +232,33 @@ unsigned long long* fresh_unit_counter(blmm_ctx* ctx) {
 }
 
 void run_scan(blmm_ctx* ctx, ScanParams P) {
+  // L2 residency experiment (BLMM_B200_L2_PERSIST = 1 | 2): a persisting access-policy window over the marker operand
+  // for the duration of the scan (2: and no per-copy cache hint in the kernel)
+  static const int l2_mode = getenv("BLMM_B200_L2_PERSIST") ? atoi(getenv("BLMM_B200_L2_PERSIST")) : 0;
+  bool window = false;
+  if (l2_mode > 0 && P.nq <= scan_max_nq(P.nk)) {
+    static bool limit_set = false;
+    int maxw = 0, maxp = 0;
+    cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    const size_t bytes = (size_t)(P.e ? P.nk : 1) * P.nq * P.p_pad * KC * 8;
+    if (!limit_set) {
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxp, (size_t)64 << 20));
+      limit_set = true;
+      if (getenv("BLMM_B200_TRACE"))
+        fprintf(stderr, "[blmm trace] L2 persisting max %d MB, window max %d MB, marker operand %.1f MB\n", maxp >> 20, maxw >> 20, bytes / 1048576.0);
+    }
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    av.accessPolicyWindow.base_ptr = const_cast<double*>(P.Mop);
+    av.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)maxw);
+    av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)std::min<size_t>((size_t)maxp, (size_t)64 << 20) / (double)bytes);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    window = cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+    cudaGetLastError();
+    P.mop_no_hint = (window && l2_mode == 2) ? 1 : 0;
+  }
   if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   if (P.nq <= scan_max_nq(P.nk)) {
     const int launched = launch_scan(P, ctx->sm_count, ctx->stream);
@@ -252,6 +279,11 @@ void run_scan(blmm_ctx* ctx, ScanParams P) {
   if (ctx->profiling) {
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->scan_timed = true;
+  }
+  if (window) {
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);  // num_bytes = 0: window off
   }
   CUDA_TRY(cudaGetLastError());
 }

@@ -6,6 +6,8 @@ the reference itself (hard part 3b)."""
 import numpy as np
 import pytest
 
+from parity_helpers import H2_TOL
+
 import blmm_oracle as orc
 from blmm_b200 import synth
 
@@ -88,7 +90,7 @@ def test_alt_grid(engine, prob, reml):
     assert np.array_equal(np.argmax(r.L, axis=0), np.argmax(ref.L, axis=0))
     # tmax! counter semantics: identical, except entries where two of the compared logL1 values tie to
     # rounding — each such entry is proven to be one (no blanket allowance)
-    from parity_helpers import assert_h2_panel_explained, H2_TOL
+    from parity_helpers import assert_h2_panel_explained
     assert_h2_panel_explained(r.h2_panel, ref.h2_panel, prof, GRID)
 
 
