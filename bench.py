@@ -416,16 +416,19 @@ def main():
                 del ins, outs
             idx = self.alt and p * (mfull / E.device_count) >= 1e8
             pcie_d2h = d2h - (p * mfull * 7 if idx else 0)
-            head = res["pageable"]
+            head = res["pinned"]
             return {"value": head["value"], "unit": "tests/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(pcie_d2h), "host_output_bytes_per_step": int(d2h),
                     "ms_per_step": head["ms_per_step"], "ms_each_step": head["ms_each_step"], "steps": steps,
-                    "buffers": "pageable", "n_gpus_in_call": E.device_count,
-                    "pinned": res["pinned"],
+                    "buffers": "pinned", "n_gpus_in_call": E.device_count,
+                    "pageable": res["pageable"],
                     "note": "ONE blocking C-ABI call on the whole problem per step, wall clock, host buffers; value = "
-                            "ordinary pageable arrays (what Julia / numpy callers pass: the library stages them through "
-                            "its pinned ring and drain threads), `pinned` = the same call on page-locked buffers (direct "
-                            "DMA).  At n_gpus > 1 the call runs on a blmm_create_multi context that shards the traits / "
+                            "page-locked host buffers as the bench contract prescribes (direct DMA into the caller's "
+                            "arrays); `pageable` = the same call on ordinary numpy arrays, what Julia / numpy callers pass "
+                            "unless they register their arrays (the library stages those through its pinned ring and "
+                            "drain threads: one extra pass over host memory, so it is bound by the host's memory "
+                            "bandwidth and stops scaling with the GPU count; DESIGN.md section 6).  "
+                            "At n_gpus > 1 the call runs on a blmm_create_multi context that shards the traits / "
                             "permutations over all GPUs itself, each GPU writing its slab of the caller's arrays over "
                             "its own PCIe link.  alt-grid: the copy-back overlaps the scan in trait-tile chunks; with "
                             ">= 1e8 panel entries per GPU the h2 panel crosses PCIe as one-byte grid indices "

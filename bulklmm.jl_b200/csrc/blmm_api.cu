@@ -232,19 +232,20 @@ unsigned long long* fresh_unit_counter(blmm_ctx* ctx) {
 }
 
 void run_scan(blmm_ctx* ctx, ScanParams P) {
-  // L2 residency experiment (BLMM_B200_L2_PERSIST = 1 | 2): a persisting access-policy window over the marker operand
-  // for the duration of the scan (2: and no per-copy cache hint in the kernel)
-  static const int l2_mode = getenv("BLMM_B200_L2_PERSIST") ? atoi(getenv("BLMM_B200_L2_PERSIST")) : 0;
+  // L2 residency of the marker operand: every trait tile re-reads all of it (47 MB at BXD size with 10 grid points), and
+  // while 4 GB of LOD / h2 panels stream through L2 the per-copy evict_last hint alone did not keep it there (ncu:
+  // 2.1 GB of DRAM reads per scan).  A persisting access-policy window over it for the duration of the launch does:
+  // 0.30 GB (profiles/l2_persist_r02.json).  BLMM_B200_L2_PERSIST = 0 switches it off, 2 also drops the per-copy hint.
+  static const int l2_mode = getenv("BLMM_B200_L2_PERSIST") ? atoi(getenv("BLMM_B200_L2_PERSIST")) : 1;
   bool window = false;
   if (l2_mode > 0 && P.nq <= scan_max_nq(P.nk)) {
-    static bool limit_set = false;
     int maxw = 0, maxp = 0;
     cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
     cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-    const size_t bytes = (size_t)(P.e ? P.nk : 1) * P.nq * P.p_pad * KC * 8;
-    if (!limit_set) {
+    const size_t bytes = (size_t)(P.e ? P.nk : (P.tile_k0 ? P.ngrid : 1)) * P.nq * P.p_pad * KC * 8;  // every slab a tile may use
+    if (!ctx->l2_limit_set) {  // per device: a multi-GPU process holds one context per GPU
       cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxp, (size_t)64 << 20));
-      limit_set = true;
+      ctx->l2_limit_set = true;
       if (getenv("BLMM_B200_TRACE"))
         fprintf(stderr, "[blmm trace] L2 persisting max %d MB, window max %d MB, marker operand %.1f MB\n", maxp >> 20, maxw >> 20, bytes / 1048576.0);
     }

@@ -64,6 +64,7 @@ struct blmm_ctx {
   int profiling = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool scan_timed = false;
+  bool l2_limit_set = false;  // persisting-L2 carve-out requested on this device
   // host results: pinned bounce ring + drain threads for pageable destinations and the h2 index panel
   blmm::HostPipe* pipe = nullptr;
   int host_threads = 0;  // 0 = default (min(16, cores - 1)); a multi-GPU parent divides the cores between its GPUs

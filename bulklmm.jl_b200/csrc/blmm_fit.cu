@@ -182,11 +182,28 @@ template <int C>
 __global__ void __launch_bounds__(32 * FIT_WARPS, C <= 2 ? 8 : (C <= 4 ? 4 : 2))
     fit_h2_kernel(const double* __restrict__ Yr, int64_t m, int n, int n_pad, int c, const double* __restrict__ C0,
                   const double* __restrict__ lambda, LikParams lik, int optim_interval, double* __restrict__ h2_out,
-                  double* __restrict__ sigma2_out, double* __restrict__ ell_out) {
+                  double* __restrict__ sigma2_out, double* __restrict__ ell_out, int staged) {
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t j = (int64_t)blockIdx.x * FIT_WARPS + wid;
+  // Brent is a chain of ~26 dependent objective evaluations, each a pass over the n weights: with the operands in
+  // shared memory (eigenvalues and covariates once per block, the trait once per warp) a pass waits on shared-memory
+  // latency instead of L1/L2 latency.  `staged` is off when the block's copies would not fit (very large n).
+  extern __shared__ double fit_sm[];
+  const double* yv = Yr + (j < m ? j : 0) * n_pad;
+  if (staged) {
+    double* lam_s = fit_sm;
+    double* c_s = lam_s + n_pad;
+    double* y_s = c_s + (int64_t)C * n_pad + (int64_t)wid * n_pad;
+    for (int l = threadIdx.x; l < n_pad; l += blockDim.x) lam_s[l] = (l < n) ? lambda[l] : 0.0;
+    for (int l = threadIdx.x; l < C * n_pad; l += blockDim.x) c_s[l] = C0[l];
+    for (int l = lane; l < n_pad; l += 32) y_s[l] = yv[l];
+    __syncthreads();
+    lambda = lam_s;
+    C0 = c_s;
+    yv = y_s;
+  }
   if (j >= m) return;
-  FitData d{Yr + j * n_pad, C0, lambda, n, n_pad, c, lane, lik, nullptr, false};
+  FitData d{yv, C0, lambda, n, n_pad, c, lane, lik, nullptr, false};
   // gridbrent: points = range(0, 1, length = optim_interval + 1); keep the first of equal minima
   double bx = 0.0, bf = INFINITY;
   for (int i = 0; i < optim_interval; ++i) {
@@ -285,10 +302,14 @@ int launch_fit_h2(const double* Yr, int64_t m, int n, int n_pad, int c, const do
                   double* ell, int* flags, cudaStream_t stream) {
   (void)flags;
   const unsigned blocks = (unsigned)((m + FIT_WARPS - 1) / FIT_WARPS);
+  const size_t smem = (size_t)(1 + c + FIT_WARPS) * n_pad * sizeof(double);
+  const int staged = smem <= 96 * 1024 ? 1 : 0;
 #define BLMM_FIT(CC)                                                                                          \
   case CC:                                                                                                    \
-    fit_h2_kernel<CC><<<blocks, 32 * FIT_WARPS, 0, stream>>>(Yr, m, n, n_pad, c, C0, lambda, lik, optim_interval, h2, \
-                                                             sigma2, ell);                                    \
+    if (staged && smem > 48 * 1024)                                                                           \
+      cudaFuncSetAttribute(fit_h2_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    fit_h2_kernel<CC><<<blocks, 32 * FIT_WARPS, staged ? smem : 0, stream>>>(Yr, m, n, n_pad, c, C0, lambda, lik, \
+                                                                              optim_interval, h2, sigma2, ell, staged); \
     break;
   switch (c) {
     BLMM_FIT(1) BLMM_FIT(2) BLMM_FIT(3) BLMM_FIT(4) BLMM_FIT(5) BLMM_FIT(6) BLMM_FIT(7) BLMM_FIT(8)

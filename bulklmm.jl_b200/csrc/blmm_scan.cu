@@ -21,6 +21,7 @@
 // serialising with it.  (bar.sync / bar.arrive pairs with a thread count do NOT order the groups on this
 // part: measured, both groups pass at once; tools/scratch notes in DESIGN.md.)
 #include <math.h>
+#include <stdlib.h>
 
 #include "blmm_kernels.cuh"
 
@@ -85,7 +86,9 @@ __device__ __forceinline__ void dmma884_zero(double& c0, double& c1, double a, d
 
 // HAS_E = false: one-element k-lists with e = 1 (null-grid bins, permutations) — no running minimum,
 // no counter, no h2 panel.  COLMAX: also reduce the per-column maximum (permutation thresholds).
-template <int NQ, bool ARGMAX, bool HAS_E, bool COLMAX>
+// TPT = marker tiles (iterations) per turn.  The one-k variants can hold the turn for two consecutive units: the
+// hand-over (~320 cycles from a group's last DMMA to the other group's first) is then paid once per two units.
+template <int NQ, bool ARGMAX, bool HAS_E, bool COLMAX, int TPT = 1>
 __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const SmemPlan plan = plan_smem(NQ);
@@ -190,6 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
   int it = 0, s = 0;
   uint32_t sphase = 0;  // parity of the ring round
   int ntop = 0, cur_tt = -1;
+  int in_turn = 0, turn_no = 0;  // TPT > 1: units done in the current turn, turns taken so far
 #ifdef BLMM_SCAN_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
@@ -238,7 +242,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
       for (int a = 0; a < 4; ++a) af[0][a] = ap[a * 8 * KC];
 #pragma unroll
       for (int b = 0; b < BT; ++b) bf[0][b] = bp[b * 8 * KC];
-      mbar_wait(my_turn, (uint32_t)it & 1u);
+      if (TPT == 1) {
+        mbar_wait(my_turn, (uint32_t)it & 1u);
+      } else if (in_turn == 0) {
+        mbar_wait(my_turn, (uint32_t)turn_no & 1u);
+      }
       TCK(1)
 #ifdef BLMM_SCAN_TIMING
       if (blockIdx.x == 0 && lane == 0 && it >= 64 && it < 128) g_scan_trace[(warp * 64 + it - 64) * 4 + 1] = tlast;
@@ -368,7 +376,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
 #pragma unroll
         for (int b = 0; b < BT; ++b) asm volatile("" ::"d"(acc[a][b][0]), "d"(acc[a][b][1]));
       __syncwarp();
-      if (lane == 0) mbar_arrive(their_turn);
+      if (TPT == 1) {
+        if (lane == 0) mbar_arrive(their_turn);
+      } else {
+        // a turn ends after TPT units, and always at the end of a trait tile (the loader of the next tile waits for
+        // every warp to leave the old one: the other group must be able to run) and at the last unit
+        ++in_turn;
+        if (in_turn == TPT || (last_of_tt && last_k) || it + 1 == total_it) {
+          if (lane == 0) mbar_arrive(their_turn);
+          in_turn = 0;
+          ++turn_no;
+        }
+      }
       // Release the stage.  The last of the NWARPS consumers refills it at once with the operands
       // of iteration it + NS, so the copy is in flight as early as the ring allows.
       if (lane == 0) {
@@ -486,11 +505,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
 #endif
 }
 
-template <int NQ, bool ARGMAX, bool HAS_E, bool COLMAX>
+template <int NQ, bool ARGMAX, bool HAS_E, bool COLMAX, int TPT = 1>
 void launch_one(const ScanParams& P, int sm_count, cudaStream_t stream) {
   const SmemPlan plan = plan_smem(NQ);
-  cudaFuncSetAttribute(scan_kernel<NQ, ARGMAX, HAS_E, COLMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  scan_kernel<NQ, ARGMAX, HAS_E, COLMAX><<<sm_count, NTHREADS, plan.bytes, stream>>>(P);
+  cudaFuncSetAttribute(scan_kernel<NQ, ARGMAX, HAS_E, COLMAX, TPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  scan_kernel<NQ, ARGMAX, HAS_E, COLMAX, TPT><<<sm_count, NTHREADS, plan.bytes, stream>>>(P);
 }
 
 template <int NQ>
@@ -502,7 +521,13 @@ void launch_nq(const ScanParams& P, int sm_count, cudaStream_t stream) {
       launch_one<NQ, false, true, false>(P, sm_count, stream);
   } else {
     // one-element k-lists (null-grid bins, permutations): the h2 panel is not produced
-    if (P.colmax)
+    static const int tpt = getenv("BLMM_B200_SCAN_TPT") ? atoi(getenv("BLMM_B200_SCAN_TPT")) : 1;
+    if (tpt == 2 && plan_smem(NQ).nstage >= 3) {
+      if (P.colmax)
+        launch_one<NQ, false, false, true, 2>(P, sm_count, stream);
+      else
+        launch_one<NQ, false, false, false, 2>(P, sm_count, stream);
+    } else if (P.colmax)
       launch_one<NQ, false, false, true>(P, sm_count, stream);
     else
       launch_one<NQ, false, false, false>(P, sm_count, stream);
