@@ -118,7 +118,7 @@ Parsed parse_csv(const char* path, char delim, int64_t skip_rows, int64_t first_
             fb = i + 1;
           }
         }
-        if (c != cols) {
+        if (c != cols || field != nfield) {  // fewer OR more fields than the first data row: readdlm would not build a matrix
           bad_row.store(r);
           bad_col.store(-2);
           return;

@@ -72,3 +72,10 @@ def test_general_selection_and_errors(tmp_path):
         f.write("h\n1,2,3\n4,5\n")
     with pytest.raises(BlmmError, match="different number of fields"):
         read_csv_matrix(ragged, skip_rows=1)
+    longer = str(tmp_path / "longer.csv")
+    with open(longer, "w") as f:
+        f.write("h\n1,2,3\n4,5,6,7\n")  # MORE fields than the first data row is ragged too
+    with pytest.raises(BlmmError, match="different number of fields"):
+        read_csv_matrix(longer, skip_rows=1)
+    with pytest.raises(BlmmError, match="different number of fields"):
+        read_csv_matrix(longer, skip_rows=1, first_col=0, col_step=1, drop_last_cols=1)
