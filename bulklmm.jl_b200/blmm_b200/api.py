@@ -431,12 +431,52 @@ def bulkscan_null(Y, G, K, Covar=None, **kw):
 def scan(y, g, K, covar=None, weights=None, prior_variance: float = 0.0, prior_sample_size: float = 0.0,
          addIntercept: bool = True, reml: bool = False, assumption: str = "null", method: str = "qr",
          optim_interval: int = 1, permutation_test: bool = False, nperms: int = 1024, rndseed: int = 0,
-         perm_idx=None, decomp_scheme: str = "eigen", decomposition=None, engine: Optional[Engine] = None):
+         perm_idx=None, decomp_scheme: str = "eigen", decomposition=None, engine: Optional[Engine] = None,
+         output_pvals: bool = False, chisq_df: int = 1, profileLL: bool = False, markerID: int = 0, h2_grid=None):
     """src/scan.jl:94-271 with permutation_test=true -> scan_perms_lite (src/scan.jl:485-557).
 
     The shuffles are drawn on the host and cross the ABI as indices (`perm_idx`, n x nperms,
     0-based).  In production the Julia shim draws them from MersenneTwister(rndseed) exactly as
-    the reference does; here numpy's generator seeded with `rndseed` stands in."""
+    the reference does; here numpy's generator seeded with `rndseed` stands in: `rndseed` is therefore NOT
+    reference-compatible in this mirror (same distribution, different stream) — pass `perm_idx` to reproduce a
+    Julia run.  `output_pvals` / `chisq_df` add `log10pvals` (src/scan.jl:353-358, 447-452; for permutations the
+    intended result instead of the reference's UndefVarError, SURVEY B2, with df = 1 as scan_perms_lite's default);
+    `profileLL` / `markerID` (1-based, as in Julia) / `h2_grid` return (results, profile) as src/scan.jl:249-266."""
+    res = _scan(y, g, K, covar, weights, prior_variance, prior_sample_size, addIntercept, reml, assumption, method,
+                optim_interval, permutation_test, nperms, rndseed, perm_idx, decomp_scheme, decomposition, engine)
+    eng = engine or default_engine()
+    if output_pvals:
+        df = 1 if permutation_test else chisq_df
+        res.log10pvals = eng.lod2log10p(res.lod, df)
+        if permutation_test:
+            res.log10Pvals_perms = eng.lod2log10p(res.L_perms, df)
+    if profileLL:
+        # profile_LL, src/analysis_helpers/single_trait_analysis.jl:46-73: null and marker-model log-likelihoods on
+        # h2_grid, no intercept added at this point (the reference rotates with addIntercept = false)
+        yv = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+        n = yv.shape[0]
+        gv = np.asarray(g, dtype=np.float64)
+        if not (1 <= markerID <= gv.shape[1]):
+            raise BlmmError(L.E_INVALID, "markerID out of range")
+        cv = np.ones((n, 1)) if covar is None else np.asarray(covar, dtype=np.float64).reshape(n, -1)
+        Kv = np.asarray(K, dtype=np.float64)
+        if weights is not None:
+            w = np.asarray(weights, dtype=np.float64)
+            cv = w[:, None] * (np.hstack([np.ones((n, 1)), cv]) if (addIntercept and covar is not None) else cv)
+            yv, gcol, Kv = w[:, None] * yv, w[:, None] * gv[:, markerID - 1:markerID], eng.weight_kinship(Kv, w)
+        else:
+            gcol = gv[:, markerID - 1:markerID]
+        U, lam, _ = eng.decompose(Kv, decomp_scheme) if decomposition is None or weights is not None else (*decomposition, 0)
+        grid = np.asarray(h2_grid, dtype=np.float64)
+        kw = dict(reml=reml, prior_variance=prior_variance, prior_sample_size=prior_sample_size)
+        prof = SimpleNamespace(ll_list_null=eng.grid_loglik(yv, cv, U, lam, grid, **kw)[:, 0],
+                               ll_list_alt=eng.grid_loglik(yv, np.hstack([cv, gcol]), U, lam, grid, **kw)[:, 0])
+        return res, prof
+    return res
+
+
+def _scan(y, g, K, covar, weights, prior_variance, prior_sample_size, addIntercept, reml, assumption, method,
+          optim_interval, permutation_test, nperms, rndseed, perm_idx, decomp_scheme, decomposition, engine):
     eng = engine or default_engine()
     y = np.asarray(y, dtype=np.float64)
     if y.ndim == 1:

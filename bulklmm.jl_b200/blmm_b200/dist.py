@@ -25,7 +25,11 @@ def all_ranges(m: int, world: int) -> List[Tuple[int, int]]:
 
 def gather_columns(local: np.ndarray, m: int, axis: int = -1):
     """All-gather column shards of unequal width into the full array on every rank.
-    `local` holds this rank's columns along `axis`.  Works on any torch.distributed backend."""
+    `local` holds this rank's columns along `axis`.  Works on any torch.distributed backend.
+    Meant for the small per-column vectors (h2_null_list, per-permutation maxima): the shards are host arrays and take a
+    round trip through the device.  For a whole LOD matrix use ONE multi-GPU context instead (`Engine(devices=[...])`,
+    blmm_create_multi): with host buffers every GPU writes its slab of the caller's array directly, and with device
+    pointers the slabs are gathered by NCCL without touching the host."""
     import torch
     import torch.distributed as dist
 

@@ -415,7 +415,7 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     // entries by default.  BLMM_B200_H2_TRANSFER = index | f64 overrides; BLMM_B200_HOST_THREADS sets the drain
     // thread count (default min(16, cores - 1), divided between the GPUs of a multi-GPU context).
     const char* h2_mode = getenv("BLMM_B200_H2_TRANSFER");
-    const bool want_idx = h2_mode ? (h2_mode[0] == 'i') : ((double)p * (double)m >= 1e8);
+    const bool want_idx = h2_mode ? (h2_mode[0] == 'i') : (ctx->idx_hint >= 0 ? ctx->idx_hint == 1 : (double)p * (double)m >= 1e8);
     const bool idx_panel = dH && want_idx && P.nq <= scan_max_nq(P.nk);
     uint8_t* dI = idx_panel ? ws<uint8_t>(ctx, S_H2IDX, (size_t)p * m) : nullptr;
     if (idx_panel && ctx->h_idx_cap < (size_t)p * m) {

@@ -67,6 +67,7 @@ struct blmm_ctx {
   bool l2_limit_set = false;  // persisting-L2 carve-out requested on this device
   // host results: pinned bounce ring + drain threads for pageable destinations and the h2 index panel
   blmm::HostPipe* pipe = nullptr;
+  int idx_hint = -1;     // multi-GPU parent: encode the h2 panel as indices (1) or not (0), decided on the WHOLE panel
   int host_threads = 0;  // 0 = default (min(16, cores - 1)); a multi-GPU parent divides the cores between its GPUs
   // several GPUs behind one context (blmm_create_multi): this context is then only the dispatcher
   blmm::MultiState* multi = nullptr;

@@ -338,8 +338,12 @@ int multi_bulkscan(blmm_ctx* parent, const blmm_problem* pr, const blmm_opts* o,
   int fr = -1;
 
   if (!dev) {
+    // the h2 panel's PCIe encoding is decided on the whole panel: what limits a multi-GPU host call is the host's
+    // ingest rate (all GPUs feed one memory system), and one-byte indices halve the bytes that cross it
+    const int idx_hint = ((double)p * (double)m >= 1e8) ? 1 : 0;
     const int rc = run_all(M, [&](int r) -> int {
       if (j1[r] == j0[r]) return BLMM_OK;
+      M->sub[r]->idx_hint = idx_hint;
       blmm_problem sp = *pr;
       sp.Y = pr->Y + j0[r] * n;
       sp.m = j1[r] - j0[r];

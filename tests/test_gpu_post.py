@@ -127,3 +127,30 @@ def test_golden_single_trait_fixture(engine):
     rb = bulkscan_null(Y[:, :8], G, K, reml=True, prior_variance=0.0, decomposition=dec, engine=engine)
     assert np.max(np.abs(rb.h2_null_list - z["bnull_h2"])) < 1e-6 and rel(rb.L, z["bnull_L"]) < 2e-5
     assert rel(lod2log10p(z["null_lod"], 1, engine=engine), z["log10p"]) < 1e-10
+
+
+def test_scan_pvals_and_profile_keywords(engine):
+    """scan's remaining keyword surface (src/scan.jl:94-109): output_pvals / chisq_df on all three branches and
+    profileLL / markerID / h2_grid (profile_LL, src/analysis_helpers/single_trait_analysis.jl:46-73)."""
+    import blmm_oracle as orc
+    from blmm_b200 import scan, synth
+    Y, G, K = synth.make_problem(79, 90, 3, seed_g=61, seed_y=62)
+    Ut, lam = orc.decompose(K)
+    dec = (np.asfortranarray(Ut.T), lam)
+    y = Y[:, 1]
+    r = scan(y, G, K, decomposition=dec, engine=engine, output_pvals=True, chisq_df=2)
+    assert np.max(np.abs(r.log10pvals - orc.lod2log10p(r.lod, 2)) / np.maximum(1.0, r.log10pvals)) < 1e-8
+    a = scan(y, G, K, assumption="alt", decomposition=dec, engine=engine, output_pvals=True)
+    assert np.max(np.abs(a.log10pvals - orc.lod2log10p(a.lod, 1)) / np.maximum(1.0, np.abs(a.log10pvals))) < 1e-8
+    perm = synth.make_perm_indices(79, 20, 1)
+    s = scan(y, G, K, permutation_test=True, perm_idx=perm, decomposition=dec, engine=engine, output_pvals=True)
+    assert s.log10Pvals_perms.shape == s.L_perms.shape
+    assert np.max(np.abs(s.log10pvals - orc.lod2log10p(s.lod, 1)) / np.maximum(1.0, s.log10pvals)) < 1e-8
+    grid = np.arange(10) / 10.0
+    res, prof = scan(y, G, K, decomposition=dec, engine=engine, reml=True, profileLL=True, markerID=7, h2_grid=grid)
+    y0, X0, l0 = orc.transform_rotation(y.reshape(-1, 1), G, K, Ut=Ut, lam=lam)
+    for k, h in enumerate(grid):
+        w = orc.make_weights(h, l0)
+        assert abs(prof.ll_list_null[k] - orc.wls(y0, X0[:, :1], w, [0.0, 0.0], reml=True).ell) < 1e-9 * 100
+        Xd = np.column_stack([X0[:, 0], X0[:, 7]])  # intercept + marker 7 (1-based) = column index 7 of [1 G]
+        assert abs(prof.ll_list_alt[k] - orc.wls(y0, Xd, w, [0.0, 0.0], reml=True).ell) < 1e-9 * 100

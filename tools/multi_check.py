@@ -46,6 +46,22 @@ def main():
     ins_h = [cm(Y), cm(G), cm(Cv), cm(U), torch.from_numpy(lam.copy())]
     ins_d = [t.to(dev0) for t in ins_h]
     out = {"gpus": nd, "n": n, "p": p, "m": m, "steps": args.steps, "workloads": {}}
+    # the ceiling of any host-buffer call at N GPUs: pinned device-to-host copies from all GPUs at once
+    nb = 1 << 29
+    hb = [torch.empty(nb, dtype=torch.uint8).pin_memory() for _ in range(nd)]
+    db = [torch.empty(nb, dtype=torch.uint8, device=f"cuda:{d}") for d in range(nd)]
+    best = 1e9
+    for _ in range(3):
+        for d in range(nd):
+            torch.cuda.synchronize(d)
+        t0 = time.perf_counter()
+        for d in range(nd):
+            hb[d].copy_(db[d], non_blocking=True)
+        for d in range(nd):
+            torch.cuda.synchronize(d)
+        best = min(best, time.perf_counter() - t0)
+    out["host_ingest_gbs_all_gpus_at_once"] = nd * nb / best / 1e9
+    del hb, db
     stream = torch.cuda.ExternalStream(many.stream, device=dev0)
 
     for name, method in (("alt-grid", L.METHOD_ALT_GRID), ("null-grid", L.METHOD_NULL_GRID)):
