@@ -64,7 +64,10 @@ void matrix_to_host(blmm_ctx* ctx, cudaStream_t stream, double* dst, int64_t ld,
     CUDA_TRY(cudaMemcpy2DAsync(dst, ld * sizeof(double), src_dev, p * sizeof(double), p * sizeof(double), cols,
                                cudaMemcpyDeviceToHost, stream));
   else
+  {
+    hostpipe_set_active(host_pipe(ctx), 1 << 30);
     hostpipe_push(host_pipe(ctx), stream, dst, ld, src_dev, p, p, cols, nullptr);
+  }
 }
 
 // Large pageable results go through the ring; small ones are not worth the hand-over.
@@ -430,6 +433,8 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     const bool L_pinned = host_ptr_is_pinned(L_out);
     const bool H_pinned = h2_out && host_ptr_is_pinned(h2_out);
     HostPipe* pipe = (idx_panel || !L_pinned || (dH && !H_pinned)) ? host_pipe(ctx) : nullptr;
+    // only index expansion to do (every Float64 copy is a direct DMA): a few drain threads, not all of them
+    hostpipe_set_active(pipe, (L_pinned && (idx_panel || !dH || H_pinned)) ? 6 : 1 << 30);
     int64_t cbeg[MAX_CHUNK + 1];
     for (int ch = 0; ch <= nchunk; ++ch)
       cbeg[ch] = std::min<int64_t>((int64_t)((int64_t)n_tiles * ch / nchunk) * SCAN_TT, m);

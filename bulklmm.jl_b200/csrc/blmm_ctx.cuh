@@ -109,6 +109,10 @@ void hostpipe_push(HostPipe* hp, cudaStream_t stream, double* dst, int64_t ld_ds
 // (`rows` x `cols`, packed) and marked with `ev`: nothing blocks, the drain threads pick it up when `ev` completes.
 void hostpipe_push_staged(HostPipe* hp, cudaEvent_t ev, double* dst, int64_t ld_dst, const void* staged, int64_t rows,
                           int64_t cols, const double* grid);
+// At most `n` drain threads take work from now on (the others sleep): expanding the index panel next to a DMA into
+// pinned result arrays needs ~6 threads and more of them only compete with the DMA for the host's memory system
+// (1 GPU: 45.3 ms with 6, 48.7 ms with 15), while moving ring slots into pageable arrays wants all of them.
+void hostpipe_set_active(HostPipe* hp, int n);
 // Blocks until every queued piece is in the caller's arrays; throws Fail on a CUDA error.
 void hostpipe_wait(HostPipe* hp);
 

@@ -93,14 +93,16 @@ struct HostPipe {
   std::string error;
   std::vector<std::thread> workers;
 
-  void worker() {
+  int active = 1 << 30;  // workers with id >= active leave the queue alone (hostpipe_set_active)
+
+  void worker(int id) {
     cudaSetDevice(device);
     for (;;) {
       Task t;
       {
         std::unique_lock<std::mutex> lk(mu);
-        cv_task.wait(lk, [&] { return quit || !tasks.empty(); });
-        if (tasks.empty()) return;
+        cv_task.wait(lk, [&] { return quit || (!tasks.empty() && id < active); });
+        if (quit && (tasks.empty() || id >= active)) return;
         t = tasks.front();
         tasks.pop_front();
       }
@@ -164,7 +166,7 @@ HostPipe* hostpipe_create(int device, int nthreads) {
     hp->free_slots.push_back(NSLOTS - 1 - i);
   }
   nthreads = std::max(1, std::min(nthreads, NSLOTS - 2));
-  for (int i = 0; i < nthreads; ++i) hp->workers.emplace_back([hp] { hp->worker(); });
+  for (int i = 0; i < nthreads; ++i) hp->workers.emplace_back([hp, i] { hp->worker(i); });
   return hp;
 }
 
@@ -223,7 +225,7 @@ void hostpipe_push(HostPipe* hp, cudaStream_t stream, double* dst, int64_t ld_ds
         std::lock_guard<std::mutex> lk(hp->mu);
         hp->tasks.push_back(Task{slot, s, hp->ev[slot], dst + c0 * ld_dst + r0, ld_dst, nr, nc, grid});
       }
-      hp->cv_task.notify_one();
+      hp->cv_task.notify_all();  // all: a sleeping worker beyond the active limit must not swallow the wake-up
     }
   }
 }
@@ -242,6 +244,15 @@ void hostpipe_push_staged(HostPipe* hp, cudaEvent_t ev, double* dst, int64_t ld_
       hp->tasks.push_back(Task{-1, src + (size_t)c0 * rows * elem, ev, dst + c0 * ld_dst, ld_dst, rows, nc, grid});
       ++hp->pending;
     }
+  }
+  hp->cv_task.notify_all();
+}
+
+void hostpipe_set_active(HostPipe* hp, int n) {
+  if (!hp) return;
+  {
+    std::lock_guard<std::mutex> lk(hp->mu);
+    hp->active = n < 1 ? 1 : n;
   }
   hp->cv_task.notify_all();
 }

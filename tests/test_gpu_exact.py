@@ -186,3 +186,25 @@ def test_null_exact_many_units_equals_sharded(engine, monkeypatch, dynamic):
     ref = orc.bulkscan_null(Y[:, idx], G, K, reml=True, prior_variance=0.0, Ut=Ut, lam=lam)
     assert np.max(np.abs(whole.h2_null_list[idx] - ref.h2_null_list)) < 1e-6
     assert np.max(np.abs(whole.L[:, idx] - ref.L) / np.maximum(1.0, np.abs(ref.L))) < 2e-5
+
+
+@pytest.mark.parametrize("n", [20, 79, 100])
+def test_scan_kernel_whole_vs_sharded_bitwise(engine, n):
+    """The shared-memory-resident scan kernel (hand-rolled mbarrier ring, last-arriver refill, ping-pong turns,
+    cross-unit prefetch) with more units than persistent CTAs (> 148) at nq = 1, 4, 5 K-chunks: a call on all traits
+    and calls on trait blocks (different unit ranges per CTA, different ring phases) must agree bit for bit, for the
+    k-loop variant (alt-grid), the one-k variant (null-grid) and the column-maximum variant (permutations)."""
+    Y, G, K, Ut, lam, dec = make(n, 1300, 1100, seed=40 + n)  # 21 marker tiles x 9 trait tiles = 189 units
+    a = bulkscan_alt_grid(Y, G, K, GRID, decomposition=dec, engine=engine)
+    r = bulkscan_null_grid(Y, G, K, GRID, decomposition=dec, engine=engine)
+    for j0, j1 in ((0, 384), (384, 1024), (1024, 1100)):
+        ab = bulkscan_alt_grid(Y[:, j0:j1], G, K, GRID, decomposition=dec, engine=engine)
+        assert np.array_equal(a.L[:, j0:j1], ab.L) and np.array_equal(a.h2_panel[:, j0:j1], ab.h2_panel)
+        rb = bulkscan_null_grid(Y[:, j0:j1], G, K, GRID, decomposition=dec, engine=engine)
+        assert np.array_equal(r.L[:, j0:j1], rb.L) and np.array_equal(r.h2_null_list[j0:j1], rb.h2_null_list)
+    perm = synth.make_perm_indices(n, 1500, rndseed=2)  # 12 column tiles x 21 marker tiles = 252 units
+    s = scan(Y[:, 0], G, K, permutation_test=True, perm_idx=perm, decomposition=dec, engine=engine)
+    for j0, j1 in ((0, 127), (127, 900), (900, 1500)):
+        sb = scan(Y[:, 0], G, K, permutation_test=True, perm_idx=perm[:, j0:j1], decomposition=dec, engine=engine)
+        assert np.array_equal(s.L_perms[:, j0:j1], sb.L_perms) and np.array_equal(s.max_lod[j0:j1], sb.max_lod)
+        assert np.array_equal(s.lod, sb.lod)

@@ -249,3 +249,42 @@ def test_multi_device_resident_perms_nccl_gather(engine, multi):
     assert np.array_equal(one.L_perms, Lp.cpu().numpy().T)
     assert np.array_equal(one.max_lod, mx.cpu().numpy())
     assert multi.last_gather_ms() > 0
+
+
+def test_multi_host_fit_scan_null_grid_loglik(engine, multi):
+    """the other per-trait entry points of a multi-GPU context (blmm_fit_h2, blmm_scan_null, blmm_grid_loglik):
+    traits sharded over the GPUs, results bit-identical to the one-GPU context"""
+    Y, G, K, U, lam = _problem(p=300, m=333, seed=27)
+    C = np.ones((79, 1))
+    for reml in (False, True):
+        a = engine.fit_h2(Y, C, U, lam, reml=reml, optim_interval=2)
+        b = multi.fit_h2(Y, C, U, lam, reml=reml, optim_interval=2)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        a = engine.grid_loglik(Y, C, U, lam, GRID, reml=reml)
+        b = multi.grid_loglik(Y, C, U, lam, GRID, reml=reml)
+        assert np.array_equal(a, b)
+    a = engine.scan_null_host(Y, G, C, U, lam, reml=True)
+    b = multi.scan_null_host(Y, G, C, U, lam, reml=True)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # entry points that do not shard run on the primary GPU and report through the parent
+    assert np.array_equal(engine.calc_kinship(G), multi.calc_kinship(G))
+    assert np.array_equal(engine.lod2log10p(a[0][:, :3], 2), multi.lod2log10p(a[0][:, :3], 2))
+    from blmm_b200 import BlmmError, _lib as L
+    with pytest.raises(BlmmError) as e:
+        multi.decompose(np.zeros((3, 4)))
+    assert e.value.code == L.E_DIM
+
+
+def test_multi_fewer_traits_than_gpus(engine, multi):
+    """m smaller than one tile per GPU: some GPUs get no columns; permutations: fewer tiles than GPUs"""
+    from blmm_b200 import bulkscan, scan, synth
+    Y, G, K, U, lam = _problem(p=100, m=5, seed=28)
+    for method in ("null-grid", "alt-grid", "null-exact"):
+        one = bulkscan(Y, G, K, method=method, h2_grid=GRID, decomposition=(U, lam), engine=engine)
+        many = bulkscan(Y, G, K, method=method, h2_grid=GRID, decomposition=(U, lam), engine=multi)
+        assert np.array_equal(one.L, many.L)
+    one = scan(Y[:, 0], G, K, permutation_test=True, nperms=0, perm_idx=np.zeros((79, 0), dtype=np.int32),
+               decomposition=(U, lam), engine=engine)
+    many = scan(Y[:, 0], G, K, permutation_test=True, nperms=0, perm_idx=np.zeros((79, 0), dtype=np.int32),
+                decomposition=(U, lam), engine=multi)
+    assert np.array_equal(one.lod, many.lod)
