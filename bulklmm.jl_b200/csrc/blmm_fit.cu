@@ -37,11 +37,16 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
   for (int i = 0; i < C; ++i) t[i] = 0.0;
   // sum_l log w_l = -log prod_l (delta lambda_l + 1): one logarithm per lane instead of one per element (the
   // running product is folded into the sum every 8 factors; a factor is at most ~2^40 for h2 <= 1 - 1e-8)
+  // Every evaluation is one link of Brent's strictly sequential chain (~26 per trait), so what counts here is the
+  // LENGTH of the dependent FP64 chain, not the operation count: reciprocals by Newton steps on the hardware estimate
+  // (5 dependent operations instead of the ~18 of the IEEE division sequence; last-bit differences are far below the
+  // rounding noise the minimiser already sees), the loop unrolled so that the elements' chains overlap.
   double yy = 0.0, slw = 0.0, prod = 1.0;
   int since = 0;
+#pragma unroll 4
   for (int l = d.lane; l < d.n; l += 32) {
     const double dl = fma(delta, d.lambda[l], 1.0);
-    const double w = d.sqrt_weights ? 1.0 / sqrt(dl) : 1.0 / dl;
+    const double w = d.sqrt_weights ? rsqrt(dl) : fast_rcp(dl);
     prod *= dl;
     if (++since == 8) {
       slw -= log(prod);
@@ -74,23 +79,30 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
   for (int i = 0; i < NT; ++i) S[i] = warp_sum(S[i]);
 #pragma unroll
   for (int i = 0; i < C; ++i) t[i] = warp_sum(t[i]);
-  // Cholesky S = L L' (packed lower, row-major), forward solve L u = t
+  // Square-root-free Cholesky S = L D L' (packed lower, row-major; Dinv = 1/D by Newton reciprocal), forward solve:
+  // t' S^-1 t = sum_a u_a^2 / D_a and log det S = sum_a log D_a (= 2 sum log of the Cholesky diagonal)
   double uu = 0.0;
-  double Lm[NT], u[C];
+  double Lm[NT], u[C], Dv[C], Dinv[C];
 #pragma unroll
   for (int a = 0; a < C; ++a) {
 #pragma unroll
     for (int b = 0; b <= a; ++b) {
       double s = S[a * (a + 1) / 2 + b];
 #pragma unroll
-      for (int k = 0; k < b; ++k) s -= Lm[a * (a + 1) / 2 + k] * Lm[b * (b + 1) / 2 + k];
-      Lm[a * (a + 1) / 2 + b] = (a == b) ? sqrt(s) : s / Lm[b * (b + 1) / 2 + b];
+      for (int k = 0; k < b; ++k) s -= Lm[a * (a + 1) / 2 + k] * Lm[b * (b + 1) / 2 + k] * Dv[k];
+      if (a == b) {
+        Dv[a] = s;
+        Dinv[a] = fast_rcp(s);
+        Lm[a * (a + 1) / 2 + a] = 1.0;
+      } else {
+        Lm[a * (a + 1) / 2 + b] = s * Dinv[b];
+      }
     }
     double s = t[a];
 #pragma unroll
     for (int k = 0; k < a; ++k) s -= Lm[a * (a + 1) / 2 + k] * u[k];
-    u[a] = s / Lm[a * (a + 1) / 2 + a];
-    uu = fma(u[a], u[a], uu);
+    u[a] = s;
+    uu = fma(s * s, Dinv[a], uu);
   }
   const double rss = yy - uu;
   const double a = d.lik.prior_a, b = d.lik.prior_b;
@@ -98,18 +110,19 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
   const double ab = a * b;
   const double denom = d.lik.reml ? ((double)(d.n - C) + pdf) : ((double)d.n + pdf);
   const double sigma2 = (rss + ab) / denom;
-  // log sigma2 and the log of the C Cholesky diagonals in ONE evaluation: lane 0 takes sigma2, lane a+1 L_aa
+  // log sigma2 and the logs of the C pivots in ONE evaluation: lane 0 takes sigma2, lane a+1 D_a
   double arg = sigma2;
 #pragma unroll
   for (int i = 0; i < C; ++i)
-    if (d.lane == i + 1) arg = Lm[i * (i + 1) / 2 + i];
+    if (d.lane == i + 1) arg = Dv[i];
   const double lg = log(arg);
   const double log_s2 = __shfl_sync(0xffffffffu, lg, 0);
   double lds = 0.0;
 #pragma unroll
   for (int i = 0; i < C; ++i) lds += __shfl_sync(0xffffffffu, lg, i + 1);
-  lds *= 2.0;
-  double ll = -0.5 * (((double)d.n + b) * log_s2 - slw + (rss + ab) / sigma2);
+  // (rss + ab) / sigma2 is `denom` up to the rounding of the division that made sigma2; the reference evaluates the
+  // quotient (src/wls.jl:84), so it is evaluated here too
+  double ll = -0.5 * (((double)d.n + b) * log_s2 - slw + (rss + ab) * fast_rcp(sigma2));
   if (d.lik.reml) ll += 0.5 * ((double)C * log_s2 - lds);
   if (sigma2_out) *sigma2_out = sigma2;
   return -ll;
