@@ -14,6 +14,40 @@ namespace {
 
 constexpr int FIT_WARPS = 4;
 
+// Natural logarithm with a SHORT dependent chain (the objective is evaluated ~26 times in sequence per trait, each
+// evaluation two logarithms deep): v = 2^e m, m in [0.75, 1.5); a 512-entry shared-memory table gives rcp ~ 1/c and
+// log c for m's interval, r = m rcp - 1 (|r| < 2^-9), log1p(r) by five terms in Estrin form: ~8 dependent FP64
+// operations instead of the ~40 of log().  Absolute error <= 1.2e-16 near 1, relative <= 5e-15 elsewhere (checked
+// against 40-digit arithmetic); operands outside the positive normal range fall back to log().
+constexpr int FIT_LTAB = 512;
+__device__ __forceinline__ void fit_build_ln_table(double2* tab, int tid, int nthreads) {
+  for (int i = tid; i < FIT_LTAB; i += nthreads) {
+    double c;
+    if (i == FIT_LTAB / 2 - 1 || i == FIT_LTAB / 2)
+      c = 1.0;
+    else if (i < FIT_LTAB / 2)
+      c = 0.75 + ((double)i + 0.5) * (0.25 / (FIT_LTAB / 2));
+    else
+      c = 1.0 + ((double)(i - FIT_LTAB / 2) + 0.5) * (0.5 / (FIT_LTAB / 2));
+    const double rcp = 1.0 / c;
+    tab[i] = make_double2(rcp, (rcp == 1.0) ? 0.0 : -log(rcp));
+  }
+}
+__device__ __forceinline__ double fit_ln(double v, const double2* __restrict__ tab) {
+  const int hi = __double2hiint(v), lo = __double2loint(v);
+  if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(v);  // zero, subnormal, negative, inf, NaN
+  const int ix = hi - 0x3fe80000;
+  const int e = ix >> 20;
+  const double m = __hiloint2double(hi - (e << 20), lo);
+  const double2 t = tab[(ix >> 11) & (FIT_LTAB - 1)];
+  const double r = fma(m, t.x, -1.0);
+  const double r2 = r * r;
+  const double p = fma(r, 1.0 / 5.0, -1.0 / 4.0);
+  const double q = fma(r, 1.0 / 3.0, -1.0 / 2.0);
+  const double lp = fma(r2, fma(r2, p, q), r);
+  return fma((double)e, 0.69314718055994530942, t.y + lp);
+}
+
 struct FitData {
   const double* y;       // trait (residualised on C0, padded), length n_pad
   const double* C0;      // [c][n_pad]
@@ -22,14 +56,21 @@ struct FitData {
   LikParams lik;
   const double* xcol;    // scan_alt: the marker column that takes the LAST covariate slot (else nullptr)
   bool sqrt_weights;     // scan_alt's final likelihoods: wls is handed sqrt(w) as its weights (src/scan.jl:440-441)
+  const double2* ltab;   // shared-memory table of fit_ln
+  double inv_denom;      // 1 / (n [- c] + prior_df): sigma2 = (rss + a b) * inv_denom
 };
+
+__device__ __forceinline__ double fit_inv_denom(const LikParams& lik, int n, int c) {
+  const double pdf = (lik.prior_b > 0.0) ? lik.prior_b + 2.0 : lik.prior_b;  // src/wls.jl:72-76
+  return 1.0 / (lik.reml ? ((double)(n - c) + pdf) : ((double)n + pdf));
+}
 
 // -ell(h2) and sigma2.  The covariate projection uses the Gram form S = C'WC, t = C'Wy,
 // rss = y'Wy - t'S^-1 t, log det S = 2 log|det R|, evaluated in one pass over the n weights.
-template <int C>
+template <int C, int UNR = 4>
 __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) {
   constexpr int NT = C * (C + 1) / 2;
-  const double delta = h2 / (1.0 - h2);
+  const double delta = h2 * fast_rcp(1.0 - h2);
   double S[NT], t[C];
 #pragma unroll
   for (int i = 0; i < NT; ++i) S[i] = 0.0;
@@ -43,13 +84,13 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
   // rounding noise the minimiser already sees), the loop unrolled so that the elements' chains overlap.
   double yy = 0.0, slw = 0.0, prod = 1.0;
   int since = 0;
-#pragma unroll 4
+#pragma unroll UNR
   for (int l = d.lane; l < d.n; l += 32) {
     const double dl = fma(delta, d.lambda[l], 1.0);
     const double w = d.sqrt_weights ? rsqrt(dl) : fast_rcp(dl);
     prod *= dl;
     if (++since == 8) {
-      slw -= log(prod);
+      slw -= fit_ln(prod, d.ltab);
       prod = 1.0;
       since = 0;
     }
@@ -71,7 +112,7 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
       }
     }
   }
-  slw -= log(prod);
+  slw -= fit_ln(prod, d.ltab);
   if (d.sqrt_weights) slw *= 0.5;
   yy = warp_sum(yy);
   slw = warp_sum(slw);
@@ -106,16 +147,14 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
   }
   const double rss = yy - uu;
   const double a = d.lik.prior_a, b = d.lik.prior_b;
-  const double pdf = (b > 0.0) ? b + 2.0 : b;
   const double ab = a * b;
-  const double denom = d.lik.reml ? ((double)(d.n - C) + pdf) : ((double)d.n + pdf);
-  const double sigma2 = (rss + ab) / denom;
+  const double sigma2 = (rss + ab) * d.inv_denom;  // 1 / denom: a per-call constant
   // log sigma2 and the logs of the C pivots in ONE evaluation: lane 0 takes sigma2, lane a+1 D_a
   double arg = sigma2;
 #pragma unroll
   for (int i = 0; i < C; ++i)
     if (d.lane == i + 1) arg = Dv[i];
-  const double lg = log(arg);
+  const double lg = fit_ln(arg, d.ltab);
   const double log_s2 = __shfl_sync(0xffffffffu, lg, 0);
   double lds = 0.0;
 #pragma unroll
@@ -130,12 +169,12 @@ __device__ double neg_loglik_c(const FitData& d, double h2, double* sigma2_out) 
 
 // Optim.jl `optimize(f, lo, hi, Brent())` with its defaults rel_tol = sqrt(eps), abs_tol = eps,
 // iterations = 1000 (call site src/gridbrent.jl:16).
-template <int C>
+template <int C, int UNR = 4>
 __device__ void brent(const FitData& d, double lo, double hi, double* xmin, double* fmin_out) {
   const double golden = 0.5 * (3.0 - sqrt(5.0));
   const double rel_tol = sqrt(DBL_EPSILON), abs_tol = DBL_EPSILON;
   double x = lo + golden * (hi - lo);
-  double fx = neg_loglik_c<C>(d, x, nullptr);
+  double fx = neg_loglik_c<C, UNR>(d, x, nullptr);
   double step = 0.0, old_step = 0.0;
   double xo = x, xoo = x, fo = fx, foo = fx;
   for (int it = 0; it < 1000; ++it) {
@@ -163,7 +202,7 @@ __device__ void brent(const FitData& d, double lo, double hi, double* xmin, doub
       step = golden * old_step;
     }
     const double xn = (fabs(step) >= tol) ? x + step : x + ((step > 0.0) ? tol : -tol);
-    const double fn = neg_loglik_c<C>(d, xn, nullptr);
+    const double fn = neg_loglik_c<C, UNR>(d, xn, nullptr);
     if (fn < fx) {
       if (xn < x)
         hi = x;
@@ -191,8 +230,10 @@ __device__ void brent(const FitData& d, double lo, double hi, double* xmin, doub
 
 // Templated on the covariate count so that the common c = 1..3 cases keep their Gram matrices in a few
 // registers (a run-time switch over all eight sizes cost 200 registers per thread: 8 warps per SM).
-template <int C>
-__global__ void __launch_bounds__(32 * FIT_WARPS, C <= 2 ? 8 : (C <= 4 ? 4 : 2))
+// BULK: many traits — occupancy hides the latency of each warp's chain (64 registers for c <= 2); otherwise (a few
+// traits: the null fit of scan / permutations) nothing hides it and the registers are better spent on no spills.
+template <int C, bool BULK>
+__global__ void __launch_bounds__(32 * FIT_WARPS, BULK ? (C <= 2 ? 8 : (C <= 4 ? 4 : 2)) : 1)
     fit_h2_kernel(const double* __restrict__ Yr, int64_t m, int n, int n_pad, int c, const double* __restrict__ C0,
                   const double* __restrict__ lambda, LikParams lik, int optim_interval, double* __restrict__ h2_out,
                   double* __restrict__ sigma2_out, double* __restrict__ ell_out, int staged) {
@@ -202,9 +243,12 @@ __global__ void __launch_bounds__(32 * FIT_WARPS, C <= 2 ? 8 : (C <= 4 ? 4 : 2))
   // shared memory (eigenvalues and covariates once per block, the trait once per warp) a pass waits on shared-memory
   // latency instead of L1/L2 latency.  `staged` is off when the block's copies would not fit (very large n).
   extern __shared__ double fit_sm[];
+  double2* ltab = reinterpret_cast<double2*>(fit_sm);
+  fit_build_ln_table(ltab, threadIdx.x, blockDim.x);
   const double* yv = Yr + (j < m ? j : 0) * n_pad;
+  if (!staged) __syncthreads();
   if (staged) {
-    double* lam_s = fit_sm;
+    double* lam_s = fit_sm + 2 * FIT_LTAB;
     double* c_s = lam_s + n_pad;
     double* y_s = c_s + (int64_t)C * n_pad + (int64_t)wid * n_pad;
     for (int l = threadIdx.x; l < n_pad; l += blockDim.x) lam_s[l] = (l < n) ? lambda[l] : 0.0;
@@ -216,21 +260,21 @@ __global__ void __launch_bounds__(32 * FIT_WARPS, C <= 2 ? 8 : (C <= 4 ? 4 : 2))
     yv = y_s;
   }
   if (j >= m) return;
-  FitData d{yv, C0, lambda, n, n_pad, c, lane, lik, nullptr, false};
+  FitData d{yv, C0, lambda, n, n_pad, c, lane, lik, nullptr, false, ltab, fit_inv_denom(lik, n, C)};
   // gridbrent: points = range(0, 1, length = optim_interval + 1); keep the first of equal minima
   double bx = 0.0, bf = INFINITY;
   for (int i = 0; i < optim_interval; ++i) {
     const double lo = (double)i / (double)optim_interval;
     const double hi = (i + 1 == optim_interval) ? 1.0 : (double)(i + 1) / (double)optim_interval;
     double x, f;
-    brent<C>(d, lo, hi, &x, &f);
+    brent<C, BULK ? 1 : 4>(d, lo, hi, &x, &f);
     if (i == 0 || f < bf) {
       bx = x;
       bf = f;
     }
   }
   double s2;
-  const double f = neg_loglik_c<C>(d, bx, &s2);
+  const double f = neg_loglik_c<C, BULK ? 1 : 4>(d, bx, &s2);
   if (lane == 0) {
     if (h2_out) h2_out[j] = bx;
     if (sigma2_out) sigma2_out[j] = s2;
@@ -265,13 +309,17 @@ __global__ void __launch_bounds__(32 * FIT_WARPS, C <= 2 ? 8 : (C <= 4 ? 4 : 2))
                     const double* __restrict__ C0, const double* __restrict__ lambda, LikParams lik,
                     int optim_interval, const double* __restrict__ ell_null, double* __restrict__ lod,
                     double* __restrict__ h2_each) {
+  __shared__ double2 ltab[FIT_LTAB];
+  fit_build_ln_table(ltab, threadIdx.x, blockDim.x);
+  __syncthreads();
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * FIT_WARPS + wid;
   if (i >= p) return;
-  FitData d{y, C0, lambda, n, n_pad, C, lane, lik, G0 + i * n_pad, false};
+  FitData d{y, C0, lambda, n, n_pad, C, lane, lik, G0 + i * n_pad, false, ltab, fit_inv_denom(lik, n, C)};
   const double h2 = fit_one<C>(d, optim_interval);
   d.sqrt_weights = true;
   d.lik.reml = 0;
+  d.inv_denom = fit_inv_denom(d.lik, n, C);
   const double ell_alt = -neg_loglik_c<C>(d, h2, nullptr);
   if (lane == 0) {
     lod[i] = (ell_alt - ell_null[0]) / 2.30258509299404568402;
@@ -284,8 +332,11 @@ template <int C>
 __global__ void scan_alt_null_kernel(const double* __restrict__ y, int n, int n_pad, const double* __restrict__ C0,
                                      const double* __restrict__ lambda, LikParams lik,
                                      const double* __restrict__ h2_null, double* __restrict__ ell_null) {
+  __shared__ double2 ltab[FIT_LTAB];
+  fit_build_ln_table(ltab, threadIdx.x, blockDim.x);
+  __syncthreads();
   lik.reml = 0;
-  FitData d{y, C0, lambda, n, n_pad, C, (int)(threadIdx.x & 31), lik, nullptr, true};
+  FitData d{y, C0, lambda, n, n_pad, C, (int)(threadIdx.x & 31), lik, nullptr, true, ltab, fit_inv_denom(lik, n, C)};
   const double e = -neg_loglik_c<C>(d, h2_null[0], nullptr);
   if (threadIdx.x == 0) ell_null[0] = e;
 }
@@ -315,14 +366,24 @@ int launch_fit_h2(const double* Yr, int64_t m, int n, int n_pad, int c, const do
                   double* ell, int* flags, cudaStream_t stream) {
   (void)flags;
   const unsigned blocks = (unsigned)((m + FIT_WARPS - 1) / FIT_WARPS);
-  const size_t smem = (size_t)(1 + c + FIT_WARPS) * n_pad * sizeof(double);
+  const size_t tab_bytes = (size_t)FIT_LTAB * sizeof(double2);
+  size_t smem = tab_bytes + (size_t)(1 + c + FIT_WARPS) * n_pad * sizeof(double);
   const int staged = smem <= 96 * 1024 ? 1 : 0;
+  if (!staged) smem = tab_bytes;
+  const bool bulk = blocks > 148 * 4;
 #define BLMM_FIT(CC)                                                                                          \
   case CC:                                                                                                    \
-    if (staged && smem > 48 * 1024)                                                                           \
-      cudaFuncSetAttribute(fit_h2_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-    fit_h2_kernel<CC><<<blocks, 32 * FIT_WARPS, staged ? smem : 0, stream>>>(Yr, m, n, n_pad, c, C0, lambda, lik, \
-                                                                              optim_interval, h2, sigma2, ell, staged); \
+    if (bulk) {                                                                                               \
+      if (smem > 48 * 1024)                                                                                   \
+        cudaFuncSetAttribute(fit_h2_kernel<CC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      fit_h2_kernel<CC, true><<<blocks, 32 * FIT_WARPS, smem, stream>>>(Yr, m, n, n_pad, c, C0, lambda, lik,  \
+                                                                        optim_interval, h2, sigma2, ell, staged); \
+    } else {                                                                                                  \
+      if (smem > 48 * 1024)                                                                                   \
+        cudaFuncSetAttribute(fit_h2_kernel<CC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      fit_h2_kernel<CC, false><<<blocks, 32 * FIT_WARPS, smem, stream>>>(Yr, m, n, n_pad, c, C0, lambda, lik, \
+                                                                         optim_interval, h2, sigma2, ell, staged); \
+    }                                                                                                         \
     break;
   switch (c) {
     BLMM_FIT(1) BLMM_FIT(2) BLMM_FIT(3) BLMM_FIT(4) BLMM_FIT(5) BLMM_FIT(6) BLMM_FIT(7) BLMM_FIT(8)
