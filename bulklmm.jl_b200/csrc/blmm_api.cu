@@ -241,7 +241,9 @@ void run_scan(blmm_ctx* ctx, ScanParams P) {
   // 0.30 GB (profiles/l2_persist_r02.json).  BLMM_B200_L2_PERSIST = 0 switches it off, 2 also drops the per-copy hint.
   static const int l2_mode = getenv("BLMM_B200_L2_PERSIST") ? atoi(getenv("BLMM_B200_L2_PERSIST")) : 1;
   bool window = false;
-  if (l2_mode > 0 && P.nq <= scan_max_nq(P.nk)) {
+  // (k-loop scans only: a one-k scan reads each marker slab once per trait tile of its bin and measured 1-3 % slower
+  // with 64 MB of L2 set aside)
+  if (l2_mode > 0 && P.e && P.nq <= scan_max_nq(P.nk)) {
     int maxw = 0, maxp = 0;
     cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
     cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
