@@ -238,7 +238,7 @@ void run_scan(blmm_ctx* ctx, ScanParams P) {
   // L2 residency of the marker operand: every trait tile re-reads all of it (47 MB at BXD size with 10 grid points), and
   // while 4 GB of LOD / h2 panels stream through L2 the per-copy evict_last hint alone did not keep it there (ncu:
   // 2.1 GB of DRAM reads per scan).  A persisting access-policy window over it for the duration of the launch does:
-  // 0.30 GB (profiles/l2_persist_r02.json).  BLMM_B200_L2_PERSIST = 0 switches it off, 2 also drops the per-copy hint.
+  // 0.30 GB (profiles/l2_persist_r02.json).  BLMM_B200_L2_PERSIST = 0 switches it off (dropping the per-copy hint as well, mode 2 of the experiment, kept 1.0 GB of reads).
   static const int l2_mode = getenv("BLMM_B200_L2_PERSIST") ? atoi(getenv("BLMM_B200_L2_PERSIST")) : 1;
   bool window = false;
   // (k-loop scans only: a one-k scan reads each marker slab once per trait tile of its bin and measured 1-3 % slower
@@ -263,7 +263,6 @@ void run_scan(blmm_ctx* ctx, ScanParams P) {
     av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     window = cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
     cudaGetLastError();
-    P.mop_no_hint = (window && l2_mode == 2) ? 1 : 0;
   }
   if (ctx->profiling) CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
   if (P.nq <= scan_max_nq(P.nk)) {

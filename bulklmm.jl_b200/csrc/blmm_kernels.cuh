@@ -154,7 +154,6 @@ struct ScanParams {
   int n_tiles_t;           // trait tiles (upper bound when n_tiles_dev is given)
   int nk;                  // k-list length of every trait tile
   int argmax_mode;         // 0 = tmax! counter semantics, 1 = arg-max index
-  int mop_no_hint;         // 1: marker-tile copies carry no L2 policy (the launch set a persisting access window instead)
   double half_n;           // n / 2
 };
 

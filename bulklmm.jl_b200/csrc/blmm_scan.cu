@@ -140,15 +140,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const ScanParams P) {
     mbar_arrive_expect_tx(&full[s], stage_bytes);
     const double* src = P.Mop + (((size_t)(k0 + kk) * NQ) * P.p_pad + (size_t)mt * MT) * KC;
     const uint64_t keep_policy = l2_evict_last_policy();
-    if (P.mop_no_hint) {
 #pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        bulk_g2s(st + (size_t)q * MT * KC, src + (size_t)q * P.p_pad * KC, marker_chunk_bytes, &full[s]);
-    } else {
-#pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        bulk_g2s_hint(st + (size_t)q * MT * KC, src + (size_t)q * P.p_pad * KC, marker_chunk_bytes, &full[s], keep_policy);
-    }
+    for (int q = 0; q < NQ; ++q)
+      bulk_g2s_hint(st + (size_t)q * MT * KC, src + (size_t)q * P.p_pad * KC, marker_chunk_bytes, &full[s], keep_policy);
     double* sc = st + (size_t)NQ * MT * KC;
     if (HAS_E) {
       bulk_g2s(sc + TT, P.et + (size_t)kk * P.tcol_pad + (size_t)tt * TT, TT * 8, &full[s]);
