@@ -97,6 +97,7 @@ struct Rotated {
   int64_t m, p;
   const double* lambda;
   const double* dU;  // the rotation matrix on the device (observation weights folded in)
+  const double* dC;  // the unrotated covariates on the device
   double *Y0, *C0, *G0;
 };
 
@@ -106,7 +107,7 @@ void rotate_markers_aside(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int
 void rotate_traits(blmm_ctx* ctx, const blmm_problem* pr, Rotated& R, int mem_space);
 
 Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool with_markers,
-                      bool with_traits = true, bool covariates_on_second_stream = false) {
+                      bool with_traits = true, bool covariates_on_second_stream = false, bool rotate_cov = true) {
   Rotated R;
   R.n = (int)pr->n;
   R.nq = num_kchunks(pr->n);
@@ -126,6 +127,7 @@ Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool
   R.dU = dU;
   R.lambda = stage_in(ctx, S_LAM, pr->lambda, n, mem_space);
   const double* dC = stage_in(ctx, S_C_IN, pr->Covar, n * R.c, mem_space);
+  R.dC = dC;
   R.C0 = ws<double>(ctx, S_C0, (size_t)R.n_pad * R.c);
   cudaStream_t cov_stream = ctx->stream;
   if (covariates_on_second_stream) {
@@ -135,7 +137,7 @@ Rotated rotate_inputs(blmm_ctx* ctx, const blmm_problem* pr, int mem_space, bool
     CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->fork_ev, 0));
     cov_stream = ctx->copy_stream;
   }
-  ctx->launches += launch_rotate(dU, dC, pr->n, R.C0, R.n_pad, R.n_pad, R.n, R.c, cov_stream);
+  if (rotate_cov) ctx->launches += launch_rotate(dU, dC, pr->n, R.C0, R.n_pad, R.n_pad, R.n, R.c, cov_stream);
   R.Y0 = nullptr;
   if (with_traits) rotate_traits(ctx, pr, R, mem_space);
   R.G0 = nullptr;
@@ -681,18 +683,36 @@ int scan_perms(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, const 
   const int64_t p = pr->p;
   const int64_t ld = o->ld_out ? o->ld_out : p;
   if (ld < p) throw Fail{BLMM_E_INVALID, "ld_out < p"};
-  Rotated R = rotate_inputs(ctx, pr, ms, true);
-  double* Yr = residualised_traits(ctx, R, o);
+  // Small n: rotation of y and the covariates, residualisation, Brent, weight constants and the null residual are ONE
+  // launch (null_fit_chain_kernel); otherwise the same steps as separate kernels.
+  const bool fused = pr->n <= 128 && !getenv("BLMM_B200_NO_CHAIN");  // test hook: force the separate kernels
+  Rotated R = rotate_inputs(ctx, pr, ms, true, !fused, false, !fused);
   double* h2 = (dev && h2_out) ? h2_out : ws<double>(ctx, S_H2V, 1);
   double* s2 = (dev && sigma2_out) ? sigma2_out : ws<double>(ctx, S_SIG2, 1);
-  ctx->launches += launch_fit_h2(Yr, 1, R.n, R.n_pad, R.c, R.C0, R.lambda, lik_of(o), o->optim_interval, h2, s2,
-                                 nullptr, ctx->d_flags, ctx->stream);
-  // transform_reweight at the fitted h2 (weight slot 0)
   WeightConsts wc = weight_ws(ctx, 1, R.n_pad, R.c);
-  ctx->launches += launch_weight_consts(h2, 1, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags, ctx->stream);
   double* z = ws<double>(ctx, S_Z, R.n_pad + 8);
   double* zrss = z + R.n_pad;
-  ctx->launches += launch_null_residual(Yr, R.n, R.n_pad, R.c, wc, z, zrss, ctx->stream);
+  bool chained = false;
+  if (fused) {
+    const double* dY = stage_in(ctx, S_Y_IN, pr->Y, (size_t)pr->n, ms);
+    double* Yr1 = ws<double>(ctx, S_YR, (size_t)R.n_pad);
+    const int launched = launch_null_fit_chain(R.dU, dY, R.dC, R.lambda, R.n, R.n_pad, R.c, lik_of(o), o->optim_interval,
+                                               R.C0, Yr1, wc, h2, s2, z, zrss, ctx->d_flags, ctx->stream);
+    ctx->launches += launched;
+    chained = launched > 0;
+    if (!chained) {  // does not apply (shared memory): rotate here and fall through to the separate kernels
+      ctx->launches += launch_rotate(R.dU, R.dC, pr->n, R.C0, R.n_pad, R.n_pad, R.n, R.c, ctx->stream);
+      rotate_traits(ctx, pr, R, ms);
+    }
+  }
+  if (!chained) {
+    double* Yr = residualised_traits(ctx, R, o);
+    ctx->launches += launch_fit_h2(Yr, 1, R.n, R.n_pad, R.c, R.C0, R.lambda, lik_of(o), o->optim_interval, h2, s2,
+                                   nullptr, ctx->d_flags, ctx->stream);
+    // transform_reweight at the fitted h2 (weight slot 0)
+    ctx->launches += launch_weight_consts(h2, 1, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags, ctx->stream);
+    ctx->launches += launch_null_residual(Yr, R.n, R.n_pad, R.c, wc, z, zrss, ctx->stream);
+  }
   const int64_t p_pad = round_up(p, SCAN_MT);
   double* Mop = ws<double>(ctx, S_MOP, (size_t)R.n_pad * p_pad);
   wait_markers(ctx, ctx->stream);  // U'G was computed on the third stream meanwhile

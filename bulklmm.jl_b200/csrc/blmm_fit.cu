@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "blmm_kernels.cuh"
+#include "blmm_prep_dev.cuh"
 
 namespace blmm {
 
@@ -341,7 +342,116 @@ __global__ void scan_alt_null_kernel(const double* __restrict__ y, int n, int n_
   if (threadIdx.x == 0) ell_null[0] = e;
 }
 
+// -----------------------------------------------------------------------------------------------
+// The whole single-trait prologue of scan(...; permutation_test = true) in ONE launch (one block of 128 threads):
+//   rotation of the trait and the covariates by U' (src/transform_helpers.jl:1-54), the unweighted residual of the
+//   trait on the covariates, fitlmm (Brent, warp 0), the weight constants at the fitted h2, and the re-weighted null
+//   residual z = P (sw .* y) of transform_reweight (src/transform_helpers.jl:57-92).
+// It replaces seven launches (rotate x2, weight constants x2, trait statistics, Brent, null residual) whose kernels take
+// 4-12 us each and whose launch gaps are as long again: a permutation step is 0.45 ms of scan, so they were a tenth
+// of it.  For n <= 128 (the rotation is done by one thread per output here).
+// -----------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128, 1)
+    null_fit_chain_kernel(const double* __restrict__ U, const double* __restrict__ y, const double* __restrict__ Cov,
+                          const double* __restrict__ lambda, int n, int n_pad, LikParams lik, int optim_interval,
+                          double* __restrict__ C0_out, double* __restrict__ Yr_out, WeightConsts wc,
+                          double* __restrict__ h2_out, double* __restrict__ sigma2_out, double* __restrict__ z_out,
+                          double* __restrict__ zrss_out, int* flags) {
+  extern __shared__ double cs[];
+  double2* ltab = reinterpret_cast<double2*>(cs);  // [FIT_LTAB]
+  double* lam_s = cs + 2 * FIT_LTAB;               // [n_pad]
+  double* c_s = lam_s + n_pad;                     // [C][n_pad]  rotated covariates
+  double* y_s = c_s + (int64_t)C * n_pad;          // [n_pad]     rotated, then residualised trait
+  __shared__ WcShared sh;
+  __shared__ double h2_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  fit_build_ln_table(ltab, tid, 128);
+  // U'[Cov y]: one thread per output, four accumulators so that the dependent chain is n / 4 long
+  for (int idx = tid; idx < (C + 1) * n_pad; idx += 128) {
+    const int col = idx / n_pad, a = idx % n_pad;
+    double v = 0.0;
+    if (a < n) {
+      const double* u = U + (int64_t)a * n;
+      const double* x = (col < C) ? Cov + (int64_t)col * n : y;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int b = 0;
+      for (; b + 4 <= n; b += 4) {
+        s0 = fma(u[b], x[b], s0);
+        s1 = fma(u[b + 1], x[b + 1], s1);
+        s2 = fma(u[b + 2], x[b + 2], s2);
+        s3 = fma(u[b + 3], x[b + 3], s3);
+      }
+      for (; b < n; ++b) s0 = fma(u[b], x[b], s0);
+      v = (s0 + s1) + (s2 + s3);
+    }
+    if (col < C) {
+      c_s[idx] = v;
+      C0_out[idx] = v;
+    } else {
+      y_s[a] = v;
+    }
+  }
+  for (int l = tid; l < n_pad; l += 128) lam_s[l] = (l < n) ? lambda[l] : 0.0;
+  __syncthreads();
+  // unweighted basis of the covariates (slot 1 of wc: w = 1), then Yr = y0 - Q Q'y0
+  weight_consts_block(true, 0.0, lam_s, c_s, n, n_pad, C, wc.w + n_pad, wc.sw + n_pad, wc.Q + (int64_t)C * n_pad,
+                      wc.slw + 1, wc.lds + 1, flags, sh);
+  if (warp == 0) {
+    double coef[MAXC];
+    proj_coefs(y_s, wc.sw + n_pad, wc.Q + (int64_t)C * n_pad, n_pad, C, lane, coef);
+    for (int l = lane; l < n_pad; l += 32) {
+      const double v = proj_elem(y_s, wc.sw + n_pad, wc.Q + (int64_t)C * n_pad, n_pad, C, l, coef);
+      y_s[l] = v;  // each lane rewrites only the elements it read last
+      Yr_out[l] = v;
+    }
+    __syncwarp();
+    FitData d{y_s, c_s, lam_s, n, n_pad, C, lane, lik, nullptr, false, ltab, fit_inv_denom(lik, n, C)};
+    const double h2 = fit_one<C>(d, optim_interval);
+    double s2;
+    neg_loglik_c<C>(d, h2, &s2);
+    if (lane == 0) {
+      h2_s = h2;
+      if (h2_out) *h2_out = h2;
+      if (sigma2_out) *sigma2_out = s2;
+    }
+  }
+  __syncthreads();
+  // transform_reweight at the fitted h2 (slot 0)
+  weight_consts_block(false, h2_s, lam_s, c_s, n, n_pad, C, wc.w, wc.sw, wc.Q, wc.slw, wc.lds, flags, sh);
+  if (warp == 0) {
+    double coef[MAXC];
+    proj_coefs(y_s, wc.sw, wc.Q, n_pad, C, lane, coef);
+    double ss = 0.0;
+    for (int l = lane; l < n_pad; l += 32) {
+      const double v = proj_elem(y_s, wc.sw, wc.Q, n_pad, C, l, coef);
+      z_out[l] = v;
+      ss = fma(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) *zrss_out = ss;
+  }
+}
+
 }  // namespace
+
+int launch_null_fit_chain(const double* U, const double* y, const double* Cov, const double* lambda, int n, int n_pad,
+                          int c, LikParams lik, int optim_interval, double* C0, double* Yr, WeightConsts wc, double* h2,
+                          double* sigma2, double* z, double* zrss, int* flags, cudaStream_t stream) {
+  const size_t smem = ((size_t)2 * FIT_LTAB + (size_t)(2 + c) * n_pad) * sizeof(double);
+  if (n > 128 || smem > 48 * 1024) return 0;
+#define BLMM_CHAIN(CC)                                                                                              \
+  case CC:                                                                                                          \
+    null_fit_chain_kernel<CC><<<1, 128, smem, stream>>>(U, y, Cov, lambda, n, n_pad, lik, optim_interval, C0, Yr, wc, \
+                                                        h2, sigma2, z, zrss, flags);                                \
+    break;
+  switch (c) {
+    BLMM_CHAIN(1) BLMM_CHAIN(2) BLMM_CHAIN(3) BLMM_CHAIN(4) BLMM_CHAIN(5) BLMM_CHAIN(6) BLMM_CHAIN(7) BLMM_CHAIN(8)
+    default: return 0;
+  }
+#undef BLMM_CHAIN
+  return 1;
+}
 
 int launch_scan_alt(const double* y, const double* G0, int64_t p, int n, int n_pad, int c, const double* C0,
                     const double* lambda, LikParams lik, int optim_interval, const double* h2_null, double* ell_null,

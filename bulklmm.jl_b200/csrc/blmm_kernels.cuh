@@ -110,6 +110,14 @@ int launch_fit_h2(const double* Yr, int64_t m, int n, int n_pad, int c, const do
                   const double* lambda, LikParams lik, int optim_interval, double* h2, double* sigma2,
                   double* ell, int* flags, cudaStream_t stream);
 
+// The single-trait prologue of scan with permutations in one launch (n <= 128; returns 0 when it does not apply and
+// the caller uses the separate launches): C0 = U'Cov (n_pad x c), Yr = residual of U'y on C0, h2 / sigma2 = fitlmm,
+// wc slot 0 = constants at h2 (slot 1 = the unweighted ones), z = P (sw .* Yr) with zrss = ||z||^2.
+// U: n x n (ld n), y: n, Cov: n x c (ld n) — unrotated device inputs.
+int launch_null_fit_chain(const double* U, const double* y, const double* Cov, const double* lambda, int n, int n_pad,
+                          int c, LikParams lik, int optim_interval, double* C0, double* Yr, WeightConsts wc, double* h2,
+                          double* sigma2, double* z, double* zrss, int* flags, cudaStream_t stream);
+
 // scan_alt (src/scan.jl:397-453) for ONE trait y (residualised, padded): per-marker Brent with covariates
 // [C0 g_i] (c + 1 <= MAXC columns), lod_i = (ell_alt_i - ell_null) / ln 10, h2_each[i] (nullable).
 // h2_null: device scalar from launch_fit_h2; ell_null: device scalar workspace.

@@ -182,3 +182,31 @@ def test_arbiter_on_worst_entries(engine):
         assert abs(h2[j] - exact) < H2_TOL and abs(ref_fit.h2 - exact) < H2_TOL
         # the likelihood is flat at the optimum: both sides' ell equal the exact maximum to rounding
         assert abs(ell[j] - float(T.ell(exact, reml=True)[0])) < 1e-9
+
+
+@pytest.mark.parametrize("ncov,reml", [(0, False), (2, True), (4, False)])
+def test_perms_fused_prologue_equals_separate_kernels(engine, monkeypatch, ncov, reml):
+    """scan with permutations at n <= 128 runs its single-trait prologue (rotation, residualisation, Brent, weight
+    constants, null residual) as ONE kernel; BLMM_B200_NO_CHAIN forces the separate kernels.  Same arithmetic up to the
+    summation order of the rotation: h2 within the Brent tolerance, LODs within 1e-8, and both within 1e-8 of the
+    oracle evaluated at their h2."""
+    n, p, nperms = 79, 300, 400
+    Y, G, K = synth.make_problem(n, p, 3, seed_g=91 + ncov, seed_y=92)
+    Ut, lam = orc.decompose(K)
+    dec = (np.asfortranarray(Ut.T), lam)
+    Z = None
+    if ncov:
+        rng = np.random.default_rng(ncov)
+        Z = np.column_stack([rng.integers(0, 2, n).astype(float)] + [rng.standard_normal(n) for _ in range(ncov - 1)])
+    perm = synth.make_perm_indices(n, nperms, 6)
+    kw = dict(permutation_test=True, perm_idx=perm, covar=Z, reml=reml, decomposition=dec, engine=engine)
+    a = scan(Y[:, 1], G, K, **kw)
+    monkeypatch.setenv("BLMM_B200_NO_CHAIN", "1")
+    b = scan(Y[:, 1], G, K, **kw)
+    monkeypatch.delenv("BLMM_B200_NO_CHAIN")
+    assert abs(a.h2_null - b.h2_null) < H2_TOL and abs(a.sigma2_e - b.sigma2_e) < 1e-6 * b.sigma2_e
+    assert rel(a.L_perms, b.L_perms) < 1e-6 and rel(a.lod, b.lod) < 1e-6
+    ref = orc.scan(Y[:, 1:2], G, K, covar=Z, permutation_test=True, perm_idx=perm, reml=reml, Ut=Ut, lam=lam)
+    assert abs(a.h2_null - ref["h2_null"]) < H2_TOL
+    assert rel(a.L_perms, ref["L_perms"]) < 1e-5 and rel(a.lod, ref["lod"]) < 1e-5
+    assert np.array_equal(a.max_lod, a.L_perms.max(axis=0))
