@@ -367,23 +367,16 @@ __global__ void __launch_bounds__(128, 1)
   __shared__ double h2_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   fit_build_ln_table(ltab, tid, 128);
-  // U'[Cov y]: one thread per output, four accumulators so that the dependent chain is n / 4 long
+  // U'[Cov y]: one thread per output
   for (int idx = tid; idx < (C + 1) * n_pad; idx += 128) {
     const int col = idx / n_pad, a = idx % n_pad;
     double v = 0.0;
     if (a < n) {
       const double* u = U + (int64_t)a * n;
       const double* x = (col < C) ? Cov + (int64_t)col * n : y;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int b = 0;
-      for (; b + 4 <= n; b += 4) {
-        s0 = fma(u[b], x[b], s0);
-        s1 = fma(u[b + 1], x[b + 1], s1);
-        s2 = fma(u[b + 2], x[b + 2], s2);
-        s3 = fma(u[b + 3], x[b + 3], s3);
-      }
-      for (; b < n; ++b) s0 = fma(u[b], x[b], s0);
-      v = (s0 + s1) + (s2 + s3);
+      // one accumulator, k ascending: the summation order of rotate_kernel, so that this path and the separate kernels
+      // (and scan without permutations) see bit-identical rotated inputs and hence the same Brent trajectory
+      for (int b = 0; b < n; ++b) v = fma(u[b], x[b], v);
     }
     if (col < C) {
       c_s[idx] = v;
