@@ -438,12 +438,24 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     HostPipe* pipe = (idx_panel || !L_pinned || (dH && !H_pinned)) ? host_pipe(ctx) : nullptr;
     // only index expansion to do (every Float64 copy is a direct DMA): a few drain threads, not all of them
     hostpipe_set_active(pipe, (L_pinned && (idx_panel || !dH || H_pinned)) ? 6 : 1 << 30);
+    // Chunk boundaries in trait tiles.  The link idles until the first chunk exists, so the first two chunks are small
+    // (1/4 and 1/2 of an even share, at least one tile) and the rest share what is left evenly.
+    int tbeg[MAX_CHUNK + 1];
+    {
+      const int even = n_tiles / nchunk;
+      const int first = std::max(1, even / 4), second = std::max(1, even / 2);
+      tbeg[0] = 0;
+      tbeg[1] = std::min(n_tiles, first);
+      tbeg[2] = std::min(n_tiles, first + second);
+      const int rest = n_tiles - tbeg[2];
+      for (int ch = 3; ch <= nchunk; ++ch) tbeg[ch] = tbeg[2] + (int)((int64_t)rest * (ch - 2) / (nchunk - 2));
+    }
     int64_t cbeg[MAX_CHUNK + 1];
-    for (int ch = 0; ch <= nchunk; ++ch)
-      cbeg[ch] = std::min<int64_t>((int64_t)((int64_t)n_tiles * ch / nchunk) * SCAN_TT, m);
+    for (int ch = 0; ch <= nchunk; ++ch) cbeg[ch] = std::min<int64_t>((int64_t)tbeg[ch] * SCAN_TT, m);
     // every chunk's scan is queued first: the copy loop below may block on ring slots
     for (int ch = 0; ch < nchunk; ++ch) {
-      const int t0 = (int)((int64_t)n_tiles * ch / nchunk), t1 = (int)((int64_t)n_tiles * (ch + 1) / nchunk);
+      const int t0 = tbeg[ch], t1 = tbeg[ch + 1];
+      if (t1 == t0) continue;
       const int64_t c0 = cbeg[ch];
       ScanParams Pc = P;
       Pc.Top = P.Top + (int64_t)t0 * SCAN_TT * KC;
@@ -459,6 +471,7 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
     }
     for (int ch = 0; ch < nchunk; ++ch) {
       const int64_t c0 = cbeg[ch], c1 = cbeg[ch + 1];
+      if (c1 == c0) continue;
       CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[ch], 0));
       // indices first: their expansion then overlaps the (8x larger) copy of the chunk's LOD columns
       if (idx_panel) {

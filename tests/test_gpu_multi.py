@@ -288,3 +288,20 @@ def test_multi_fewer_traits_than_gpus(engine, multi):
     many = scan(Y[:, 0], G, K, permutation_test=True, nperms=0, perm_idx=np.zeros((79, 0), dtype=np.int32),
                 decomposition=(U, lam), engine=multi)
     assert np.array_equal(one.lod, many.lod)
+
+
+def test_contexts_come_and_go(engine):
+    """contexts (single and multi-GPU) can be created, used and destroyed repeatedly, and several can coexist:
+    worker threads, drain threads, streams, pinned rings and NCCL communicators are released with them"""
+    from blmm_b200 import Engine, bulkscan
+    Y, G, K, U, lam = _problem(p=200, m=300, seed=31)
+    ref = bulkscan(Y, G, K, method="alt-grid", h2_grid=GRID, decomposition=(U, lam), engine=engine)
+    devs = list(range(min(_ngpu(), 2)))
+    for rep in range(3):
+        e1 = Engine(0)
+        e2 = Engine(devices=devs) if len(devs) > 1 else Engine(0)
+        for e in (e1, e2):
+            r = bulkscan(Y, G, K, method="alt-grid", h2_grid=GRID, decomposition=(U, lam), engine=e)
+            assert np.array_equal(r.L, ref.L) and np.array_equal(r.h2_panel, ref.h2_panel)
+        e2.close()
+        e1.close()
