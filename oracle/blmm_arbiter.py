@@ -1,6 +1,6 @@
 """Arbiter for parity disputes: the same reference formulas as blmm_oracle.py, evaluated in higher precision.
 
-TEST INFRASTRUCTURE ONLY (like blmm_oracle.py): imported by tests/ and tools/arbiter_report.py, never by the
+TEST INFRASTRUCTURE ONLY (like blmm_oracle.py): imported by tests/ and tests/arbiter_report.py, never by the
 product.  SURVEY section 7 step 1 / section 8c ask for it: when the float64 oracle and the CUDA engine disagree near the 1e-8
 tolerance, neither is "right" by construction (both round); the arbiter says which is closer to the exact value of
 the reference's formula on the same float64 inputs.

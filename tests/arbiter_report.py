@@ -1,6 +1,6 @@
 """Which side is closer to the exact value when the CUDA engine and the float64 oracle disagree?  
 
-    python tools/arbiter_report.py > profiles/arbiter_r02.json          (on a B200 box)
+    python tests/arbiter_report.py > profiles/arbiter_r02.json          (on a B200 box)
 
 For alt-grid, null-grid and null-exact LODs on a seeded synthetic problem (n = 79, real BXD kinship spectrum shape):
 the entries with the largest |engine - oracle| are re-evaluated in 50-digit arithmetic (oracle/blmm_arbiter.py) from the

@@ -5,7 +5,7 @@ tests/golden/make_reference_fixtures.jl, under Julia.  Same file names and shape
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import blmm_oracle as orc
