@@ -1,7 +1,7 @@
 """Ad-hoc device-resident timing of the BXD-shape scans (development aid; bench.py is the contract)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "bulklmm.jl_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "bulklmm.jl_b200"))
 import numpy as np, torch
 from blmm_b200 import Engine, synth, _lib as L
 
