@@ -210,3 +210,49 @@ def test_perms_fused_prologue_equals_separate_kernels(engine, monkeypatch, ncov,
     assert abs(a.h2_null - ref["h2_null"]) < H2_TOL
     assert rel(a.L_perms, ref["L_perms"]) < 1e-5 and rel(a.lod, ref["lod"]) < 1e-5
     assert np.array_equal(a.max_lod, a.L_perms.max(axis=0))
+
+
+def test_full_bxd_shape_equivariance_properties(engine):
+    """BASELINE.json's full BXD shape (n=79, p=7321, m=35554) through size-independent properties of the path:
+      * permuting the trait columns permutes the columns of L / h2 bit for bit (every (marker, trait) entry is
+        computed independently of its neighbours: tiles, bins, chunks and CTA unit ranges all change);
+      * permuting the markers permutes the rows bit for bit;
+      * an affine change of a trait's units (a*y + b, a > 0) leaves its LODs unchanged (to rounding) and its grid h2 exact;
+      * null-exact on all traits equals the oracle on a random sample of columns at the engine's h2."""
+    n, p, m = synth.BXD_N, synth.BXD_P, synth.BXD_M
+    Y, G, K = synth.make_problem(n, p, m)
+    U, lam, _ = engine.decompose(K)
+    dec = (U, lam)
+    rng = np.random.default_rng(5)
+    base = bulkscan_null_grid(Y, G, K, GRID, decomposition=dec, engine=engine)
+    pt = rng.permutation(m)
+    r = bulkscan_null_grid(Y[:, pt], G, K, GRID, decomposition=dec, engine=engine)
+    assert np.array_equal(r.L, base.L[:, pt]) and np.array_equal(r.h2_null_list, base.h2_null_list[pt])
+    del r
+    pm = rng.permutation(p)
+    r = bulkscan_null_grid(Y, G[:, pm], K, GRID, decomposition=dec, engine=engine)
+    assert np.array_equal(r.L, base.L[pm, :]) and np.array_equal(r.h2_null_list, base.h2_null_list)
+    del r
+    a = rng.uniform(0.5, 20.0, m)
+    b = rng.uniform(-5.0, 5.0, m)
+    r = bulkscan_null_grid(Y * a[None, :] + b[None, :], G, K, GRID, prior_variance=0.0, decomposition=dec, engine=engine)
+    base0 = bulkscan_null_grid(Y, G, K, GRID, prior_variance=0.0, decomposition=dec, engine=engine)
+    assert np.array_equal(r.h2_null_list, base0.h2_null_list)
+    assert rel(r.L, base0.L) < 1e-8
+    del r, base0, base
+    # alt-grid: same column equivariance for both outputs
+    sub = rng.choice(m, size=6000, replace=False)
+    alt = bulkscan_alt_grid(Y, G, K, GRID, decomposition=dec, engine=engine)
+    alt_sub = bulkscan_alt_grid(Y[:, sub], G, K, GRID, decomposition=dec, engine=engine)
+    assert np.array_equal(alt_sub.L, alt.L[:, sub]) and np.array_equal(alt_sub.h2_panel, alt.h2_panel[:, sub])
+    del alt, alt_sub
+    # null-exact at full size against the oracle on a sample of columns
+    ex = bulkscan_null(Y, G, K, reml=True, prior_variance=0.0, decomposition=dec, engine=engine)
+    cols = rng.choice(m, size=32, replace=False)
+    Ut = np.ascontiguousarray(U.T)
+    ref = orc.bulkscan_null(Y[:, cols], G, K, reml=True, prior_variance=0.0, Ut=Ut, lam=lam,
+                            h2_override=ex.h2_null_list[cols])
+    assert rel(ex.L[:, cols], ref.L) < TOL
+    assert np.array_equal(np.argmax(ex.L[:, cols], axis=0), np.argmax(ref.L, axis=0))
+    ref_h2 = orc.bulkscan_null(Y[:, cols[:8]], G[:, :2], K, reml=True, prior_variance=0.0, Ut=Ut, lam=lam)
+    assert np.max(np.abs(ex.h2_null_list[cols[:8]] - ref_h2.h2_null_list)) < H2_TOL
