@@ -320,10 +320,15 @@ int bulkscan_grid(blmm_ctx* ctx, const blmm_problem* pr, const blmm_opts* o, dou
   WeightConsts wc = weight_ws(ctx, nk, num_kchunks(pr->n) * KC, (int)pr->c);
   // second stream: covariate rotation -> weight constants -> marker rotation -> marker operand;
   // main stream: trait rotation, then (after the weight constants) the trait statistics
-  Rotated R = rotate_inputs(ctx, pr, ms, false, false, true);
+  const bool rot_in_wc = pr->n <= 128;  // small n: the covariate rotation is folded into the weight-constant blocks
+  Rotated R = rotate_inputs(ctx, pr, ms, false, false, true, !rot_in_wc);
   rotate_markers_aside(ctx, pr, R, ms, ctx->stream);  // third stream: G -> U'G beside the covariate chain
-  ctx->launches += launch_weight_consts(d_grid, nk, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags,
-                                        ctx->copy_stream);
+  if (rot_in_wc)
+    ctx->launches += launch_weight_consts_rot(d_grid, nk, R.lambda, R.dU, R.dC, R.n, R.n_pad, R.c, wc, R.C0,
+                                              ctx->d_flags, ctx->copy_stream);
+  else
+    ctx->launches += launch_weight_consts(d_grid, nk, R.lambda, R.C0, R.n, R.n_pad, R.c, wc, ctx->d_flags,
+                                          ctx->copy_stream);
   CUDA_TRY(cudaEventRecord(ctx->wc_ev, ctx->copy_stream));
   fork_marker_side(ctx, pr, R, ms, nk, wc, true, Mop, p_pad, true);
   rotate_traits(ctx, pr, R, ms);

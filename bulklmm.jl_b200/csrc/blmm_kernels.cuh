@@ -39,6 +39,11 @@ struct WeightConsts {
 int launch_weight_consts(const double* h2_dev, int nk, const double* lambda, const double* C0, int n,
                          int n_pad, int c, WeightConsts wc, int* flags, cudaStream_t stream);
 
+// The same from the UNROTATED covariates (Cov: n x c, ld n) for n <= 128: each block rotates them by U' itself and block 0
+// also writes C0; returns 0 (nothing launched) for larger n.
+int launch_weight_consts_rot(const double* h2_dev, int nk, const double* lambda, const double* U, const double* Cov,
+                             int n, int n_pad, int c, WeightConsts wc, double* C0, int* flags, cudaStream_t stream);
+
 struct LikParams {  // wls / wls_multivar scalars, src/wls.jl:72-92, 150-170
   double prior_a, prior_b;
   int reml;

@@ -164,6 +164,35 @@ __global__ void __launch_bounds__(128) weight_consts_kernel(const double* __rest
                       wc.sw + (int64_t)k * n_pad, wc.Q + (int64_t)k * c * n_pad, wc.slw + k, wc.lds + k, flags, sh);
 }
 
+// The same with the rotation of the covariates folded in (n <= 128): every block rotates the c covariate columns itself
+// (one thread per output, k ascending: rotate_kernel's summation order, so C0 is bit-identical) instead of waiting for
+// a separate launch; the covariate rotation sat at the head of the marker-side critical path of every grid scan.
+__global__ void __launch_bounds__(128) weight_consts_rot_kernel(const double* __restrict__ h2_dev, int nk,
+                                                                const double* __restrict__ lambda,
+                                                                const double* __restrict__ U,
+                                                                const double* __restrict__ Cov, int n, int n_pad, int c,
+                                                                WeightConsts wc, double* __restrict__ C0_out,
+                                                                int* flags) {
+  extern __shared__ double c_s[];  // [c][n_pad]
+  __shared__ WcShared sh;
+  for (int idx = threadIdx.x; idx < c * n_pad; idx += 128) {
+    const int col = idx / n_pad, a = idx % n_pad;
+    double v = 0.0;
+    if (a < n) {
+      const double* u = U + (int64_t)a * n;
+      const double* x = Cov + (int64_t)col * n;
+      for (int b = 0; b < n; ++b) v = fma(u[b], x[b], v);
+    }
+    c_s[idx] = v;
+    if (blockIdx.x == 0) C0_out[idx] = v;
+  }
+  __syncthreads();
+  const int k = blockIdx.x;
+  const bool ols = (k == nk);
+  weight_consts_block(ols, ols ? 0.0 : h2_dev[k], lambda, c_s, n, n_pad, c, wc.w + (int64_t)k * n_pad,
+                      wc.sw + (int64_t)k * n_pad, wc.Q + (int64_t)k * c * n_pad, wc.slw + k, wc.lds + k, flags, sh);
+}
+
 // ell of wls / wls_multivar (src/wls.jl:72-92) from the weighted rss
 __device__ __forceinline__ double null_loglik(double rss, double slw, double lds, int n, int c, LikParams lik,
                                               double* sigma2_out) {
@@ -716,6 +745,14 @@ int launch_kinship(const double* G, int n, int64_t p, double* K, double* partial
 int launch_weight_consts(const double* h2_dev, int nk, const double* lambda, const double* C0, int n,
                          int n_pad, int c, WeightConsts wc, int* flags, cudaStream_t stream) {
   weight_consts_kernel<<<nk + 1, 128, 0, stream>>>(h2_dev, nk, lambda, C0, n, n_pad, c, wc, flags);
+  return 1;
+}
+
+int launch_weight_consts_rot(const double* h2_dev, int nk, const double* lambda, const double* U, const double* Cov,
+                             int n, int n_pad, int c, WeightConsts wc, double* C0, int* flags, cudaStream_t stream) {
+  if (n > 128) return 0;
+  weight_consts_rot_kernel<<<nk + 1, 128, (size_t)c * n_pad * sizeof(double), stream>>>(h2_dev, nk, lambda, U, Cov, n,
+                                                                                         n_pad, c, wc, C0, flags);
   return 1;
 }
 
