@@ -21,12 +21,39 @@ using namespace blmm;
 
 namespace {
 
-// device view of an input matrix: the caller's pointer (device mode) or a staged copy (host mode)
+HostPipe* host_pipe(blmm_ctx* ctx);
+
+// device view of an input matrix: the caller's pointer (device mode) or a staged copy (host mode).  Large pageable
+// inputs are first gathered into a pinned arena by the drain threads (see hostpipe_gather_input); the arena is reset
+// at the start of every call (host-buffer calls return only when all their copies are complete).
 const double* stage_in(blmm_ctx* ctx, Slot s, const double* p, size_t count, int mem_space,
                        cudaStream_t stream = nullptr) {
   if (mem_space == BLMM_MEM_DEVICE) return p;
   double* d = ws<double>(ctx, s, count);
-  CUDA_TRY(cudaMemcpyAsync(d, p, count * sizeof(double), cudaMemcpyHostToDevice, stream ? stream : ctx->stream));
+  const size_t bytes = count * sizeof(double);
+  cudaStream_t st = stream ? stream : ctx->stream;
+  const void* src = p;
+  if (bytes >= ((size_t)2 << 20) && !host_ptr_is_pinned(p)) {
+    const size_t need = ctx->h_in_off + bytes;
+    if (need > ctx->h_in_cap) {
+      // earlier regions may still be feeding copies: let them finish before the arena moves
+      CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      CUDA_TRY(cudaStreamSynchronize(ctx->copy_stream));
+      CUDA_TRY(cudaStreamSynchronize(ctx->aux_stream));
+      if (ctx->h_in) CUDA_TRY(cudaFreeHost(ctx->h_in));
+      ctx->h_in = nullptr;
+      ctx->h_in_cap = 0;
+      ctx->h_in_off = 0;
+      const size_t cap = std::max(bytes + bytes / 2, (size_t)32 << 20);
+      CUDA_TRY(cudaMallocHost(&ctx->h_in, cap));
+      ctx->h_in_cap = cap;
+    }
+    uint8_t* region = ctx->h_in + ctx->h_in_off;
+    ctx->h_in_off += (bytes + 255) & ~(size_t)255;
+    hostpipe_gather_input(host_pipe(ctx), region, p, bytes);
+    src = region;
+  }
+  CUDA_TRY(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
   return d;
 }
 
@@ -968,6 +995,7 @@ int guarded(blmm_ctx* ctx, F&& f) {
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) throw Fail{BLMM_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
     ctx->err.clear();
+    ctx->h_in_off = 0;  // every earlier host-buffer call has completed its copies
     return f();
   } catch (const Fail& fl) {
     ctx->err = fl.msg;
@@ -1087,6 +1115,7 @@ void blmm_destroy(blmm_ctx* ctx) {
     if (ctx->idx_ev[i]) cudaEventDestroy(ctx->idx_ev[i]);
   }
   if (ctx->h_idx) cudaFreeHost(ctx->h_idx);
+  if (ctx->h_in) cudaFreeHost(ctx->h_in);
   if (ctx->aux_fork_ev) cudaEventDestroy(ctx->aux_fork_ev);
   if (ctx->aux_done_ev) cudaEventDestroy(ctx->aux_done_ev);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);

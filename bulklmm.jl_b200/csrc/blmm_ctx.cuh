@@ -53,6 +53,8 @@ struct blmm_ctx {
   cudaEvent_t idx_ev[blmm::MAX_CHUNK] = {};  // chunk's h2 index panel has landed in h_idx
   uint8_t* h_idx = nullptr;                   // pinned staging of the h2 index panel (host-buffer alt-grid calls)
   size_t h_idx_cap = 0;
+  uint8_t* h_in = nullptr;                    // pinned arena for large pageable inputs of the current call
+  size_t h_in_cap = 0, h_in_off = 0;
   cudaEvent_t fork_ev = nullptr, join_ev = nullptr, wc_ev = nullptr;  // marker-side preprocessing on copy_stream
   cusolverDnHandle_t solver = nullptr;
   void* buf[blmm::S_COUNT] = {};
@@ -109,6 +111,11 @@ void hostpipe_push(HostPipe* hp, cudaStream_t stream, double* dst, int64_t ld_ds
 // (`rows` x `cols`, packed) and marked with `ev`: nothing blocks, the drain threads pick it up when `ev` completes.
 void hostpipe_push_staged(HostPipe* hp, cudaEvent_t ev, double* dst, int64_t ld_dst, const void* staged, int64_t rows,
                           int64_t cols, const double* grid);
+// Input side of the same problem: a host-to-device copy from pageable memory is staged by the runtime on the calling
+// thread (one memcpy thread, ~7 GB/s: 3 ms for the 22 MB trait matrix in front of everything else).  The drain threads
+// copy `bytes` from `src` into the pinned buffer `pinned_dst` in parallel; returns when the copy is complete (nothing
+// else may be queued on the pipe meanwhile).
+void hostpipe_gather_input(HostPipe* hp, void* pinned_dst, const void* src, size_t bytes);
 // At most `n` drain threads take work from now on (the others sleep): expanding the index panel next to a DMA into
 // pinned result arrays needs ~6 threads and more of them only compete with the DMA for the host's memory system
 // (1 GPU: 45.3 ms with 6, 48.7 ms with 15), while moving ring slots into pageable arrays wants all of them.

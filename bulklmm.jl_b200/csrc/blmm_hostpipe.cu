@@ -36,6 +36,7 @@ struct Task {
   int64_t rows;      // elements per column in this piece
   int64_t cols;
   const double* grid;  // nullptr: Float64 copy; else expansion of one-byte indices
+  void* in_dst = nullptr;  // host-to-host piece of an input upload (hostpipe_gather_input): memcpy(in_dst, src, rows bytes)
 };
 
 // dst[0..n) = src[0..n) with streaming stores (dst 8-byte aligned)
@@ -105,6 +106,15 @@ struct HostPipe {
         if (quit && (tasks.empty() || id >= active)) return;
         t = tasks.front();
         tasks.pop_front();
+      }
+      if (t.in_dst) {  // input upload: plain host copy into pinned staging, no event to wait for
+        memcpy(t.in_dst, t.src, (size_t)t.rows);
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          --pending;
+        }
+        cv_done.notify_all();
+        continue;
       }
       const cudaError_t e = cudaEventSynchronize(t.ev);
       if (e == cudaSuccess) {
@@ -246,6 +256,26 @@ void hostpipe_push_staged(HostPipe* hp, cudaEvent_t ev, double* dst, int64_t ld_
     }
   }
   hp->cv_task.notify_all();
+}
+
+void hostpipe_gather_input(HostPipe* hp, void* pinned_dst, const void* src, size_t bytes) {
+  constexpr size_t PIECE = 1u << 20;
+  {
+    std::lock_guard<std::mutex> lk(hp->mu);
+    hp->active = 1 << 30;
+    for (size_t off = 0; off < bytes; off += PIECE) {
+      Task t{};
+      t.slot = -1;
+      t.src = static_cast<const uint8_t*>(src) + off;
+      t.rows = (int64_t)std::min(PIECE, bytes - off);
+      t.in_dst = static_cast<uint8_t*>(pinned_dst) + off;
+      hp->tasks.push_back(t);
+      ++hp->pending;
+    }
+  }
+  hp->cv_task.notify_all();
+  std::unique_lock<std::mutex> lk(hp->mu);
+  hp->cv_done.wait(lk, [&] { return hp->pending == 0; });
 }
 
 void hostpipe_set_active(HostPipe* hp, int n) {
