@@ -438,6 +438,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
   double* T = smem;                                       // [nbatch][n_pad][32]  (lane-contiguous)
   double* Tt = T + (size_t)nbatch * n_pad * 32;           // [nbatch][32][n_pad]  (l-contiguous)
   double* gbase = Tt + (size_t)nbatch * n_pad * 32;       // [WARPS_PER_BLOCK][2][n_pad]
+  // [n_pad] offset of element l inside one k-slab for marker 0: (l / KC) p_pad KC + l % KC (marker i adds i KC)
+  int64_t* off_s = reinterpret_cast<int64_t*>(gbase + (size_t)WARPS_PER_BLOCK * 2 * n_pad);
+  for (int l = threadIdx.x; l < n_pad; l += blockDim.x) off_s[l] = (int64_t)(l / KC) * p_pad * KC + (l % KC);
   for (int idx = threadIdx.x; idx < nbatch * n_pad * 32; idx += blockDim.x) {
     const int v = idx & 31, l = (idx >> 5) % n_pad, bt = (idx >> 5) / n_pad;
     const int a = v / KB, k = bt * KB + v % KB;
@@ -493,19 +496,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, 4)
       const double inv_mine = 1.0 / nrm;  // meaningful in lanes (0, kk)
       const int kcount = (nk - bt * KB) < KB ? (nk - bt * KB) : KB;
       const double* Ttb = Tt + (size_t)bt * 32 * n_pad;
+      // this lane's destination offsets inside one k-slab do not depend on k: no division in the store loop
+      // (ncu: the kernel was bound by the integer instructions of its index arithmetic, not by FP64 or memory)
+      const int64_t slab = (int64_t)nq * p_pad * KC;
       for (int kk = 0; kk < kcount; ++kk) {
         const double inv = __shfl_sync(0xffffffffu, inv_mine, kk);
         double tk[MAXC];
 #pragma unroll
         for (int a = 0; a < MAXC; ++a)
           if (a < c) tk[a] = __shfl_sync(0xffffffffu, sv, ((a + 1) * KB + kk) & 31);
-        const int k = bt * KB + kk;
+        double* out_k = Mop + (int64_t)(bt * KB + kk) * slab + i * KC;
+        const double* wk = Ttb + (size_t)kk * n_pad;
         for (int l2 = lane; l2 < n_pad; l2 += 32) {
-          double z = Ttb[(size_t)kk * n_pad + l2] * gb[l2];  // w_k g
+          double z = wk[l2] * gb[l2];  // w_k g
 #pragma unroll
           for (int a = 0; a < MAXC; ++a)
             if (a < c) z = fma(-Ttb[((size_t)(a + 1) * KB + kk) * n_pad + l2], tk[a], z);
-          Mop[(((int64_t)k * nq + l2 / KC) * p_pad + i) * KC + (l2 % KC)] = z * inv;
+          out_k[off_s[l2]] = z * inv;
         }
       }
     }
@@ -799,7 +806,7 @@ int launch_marker_operand(const double* G0, int64_t p, int64_t p_pad, int n, int
     // table form when the block's tables fit in shared memory (BXD-size grid scans: 50 KB)
     const int KB = 32 / (1 + c);
     const int nbatch = (nk + KB - 1) / KB;
-    const size_t tsmem = ((size_t)2 * nbatch * n_pad * 32 + (size_t)WARPS_PER_BLOCK * 2 * n_pad) * sizeof(double);
+    const size_t tsmem = ((size_t)2 * nbatch * n_pad * 32 + (size_t)WARPS_PER_BLOCK * 2 * n_pad + (size_t)n_pad) * sizeof(double);
     if (tsmem <= 56 * 1024) {
       if (tsmem > 48 * 1024)
         cudaFuncSetAttribute(marker_operand_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
